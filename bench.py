@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: LS + (interp) + real/imag FC denoiser, BASELINE.json metric
+"channel-estimates/sec (32x4, 1024-sc pkts)", one channel estimate = one packet's full H-hat.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # our arm (prints ONE JSON line)
+    python bench.py --impl reference --steps 3 --warmup 1     # CPU restatement of the reference, same metric
+    torchrun ... bench.py --gpus N ...                        # N ranks, packets sharded, all-gather of H-hat
+
+A step = one pass of the whole path over one 500-packet batch per GPU (configs[1] of BASELINE.json).
+`value`  : packets/s with Y resident in HBM (device pointers through the C ABI), CUDA events, max over ranks.
+`e2e`    : same metric through the same C-ABI call with pinned HOST buffers; H2D of Y and D2H of both planes
+           inside the timed region (the library overlaps them with compute in chunks).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT, NR, NSC, HIDDEN, SNR_DB = 32, 4, 1024, (1024, 1024), 10.0
+WORKLOAD = "configs[1]: Nt=32 Nr=4, 1024 sc, 500-packet batch, SNR=10 dB, FC 1024-1024-1024-1024 x2 nets"
+MLP_FLOP_PER_PKT = NT * NR * 2 * 2 * (NSC * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * NSC)
+LS_BYTES_PER_PKT = NR * NT * NSC * 8 * 2                                                            # Y in + H planes out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU restatement (reference arm)
+def cpu_reference_run(n_pkt_sample, steps, warmup):
+    """The reference's own path restated on the host cores (MATLAB/TF cannot run here: SURVEY 8c):
+    LS in complex128 (helperMIMOChannelEstimate.m:33-36, one batched matmul per packet) and the two Keras
+    nets as torch CPU FP32 with batch = Nt*Nr per predict call (..._DNN.py:339), all host threads."""
+    import torch
+    from oracle import ls as o_ls, mlp as o_mlp
+    import mamimo_b200_synth as synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = synth.make_pilots(NSC)
+    nets = synth.make_nets(NSC, HIDDEN, NSC)
+    P = synth.sylvester(NT)
+    Y, _ = synth.make_packets(1, n_pkt_sample, NT, NR, NSC, SNR_DB, x_tones=x)
+    Yt = torch.from_numpy(Y)
+    tnets = {}
+    for name in ("real", "imag"):
+        tnets[name] = [(torch.from_numpy(np.asarray(L["W"], np.float32)), torch.from_numpy(np.asarray(L["b"], np.float32)),
+                        None if L["bn"] is None else [torch.from_numpy(np.asarray(t, np.float32)) for t in L["bn"]])
+                       for L in nets[name]]
+
+    def predict(layers, xin):
+        h = xin
+        for i, (W, b, bn) in enumerate(layers):
+            h = torch.addmm(b, h, W)
+            if i < len(layers) - 1:
+                h = torch.relu(h)
+                if bn is not None:
+                    g, be, mu, var = bn
+                    h = g * (h - mu) / torch.sqrt(var + o_mlp.BN_EPS) + be
+        return h
+
+    def one_step():
+        for p in range(n_pkt_sample):
+            with torch.no_grad():
+                H = o_ls.ls_estimate_torch(Yt[p:p + 1], P, x)      # complex128, as MATLAB computes
+                X = H.reshape(-1, NSC)
+                predict(tnets["real"], X.real.to(torch.float32))
+                predict(tnets["imag"], X.imag.to(torch.float32))
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_pkt_sample / dt, dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.cpu_sample
+    val, dt, cores = cpu_reference_run(n_sample, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": "channel-estimates/sec (32x4, 1024-sc pkts)", "value": val, "unit": "packets/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 LS + f32 FC (CPU)",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_pkts_per_step": n_sample},
+        "cpu_baseline": {"value": val, "unit": "packets/s", "cores": cores, "kind": "port",
+                         "sample": "%d packets per step (torch-CPU c128 LS + fp32 FC, batch=Nt*Nr per predict)" % n_sample},
+        "e2e": {"value": val, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mamimo_b200 as mm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a B200: no CUDA device visible, and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    npkt = args.npkt
+    x = mm.synth.make_pilots(NSC)
+    nets = mm.synth.make_nets(NSC, HIDDEN, NSC)
+    # per-rank packet shard: rank r owns global packets [r*npkt, (r+1)*npkt)  (weak scaling)
+    gen_pkts = min(npkt, args.gen_pkts)
+    Yg, _ = mm.synth.make_packets(1, gen_pkts, NT, NR, NSC, SNR_DB, x_tones=x, first_pkt=rank * npkt)
+    reps = (npkt + gen_pkts - 1) // gen_pkts
+    Yh = torch.from_numpy(np.concatenate([Yg] * reps)[:npkt].copy()).pin_memory()
+    Yd = Yh.to(dev)
+    rows = npkt * NT * NR
+    Hr = torch.empty((rows, NSC), dtype=torch.float32, device=dev)
+    Hi = torch.empty_like(Hr)
+    Hr_h = torch.empty((rows, NSC), dtype=torch.float32).pin_memory()
+    Hi_h = torch.empty((rows, NSC), dtype=torch.float32).pin_memory()
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty((world * rows, NSC), dtype=torch.float32, device=dev) for _ in range(2)]
+
+    eng = mm.Engine(NT, NR, NSC, hidden=HIDDEN, precision=args.precision, max_pkts=args.max_pkts, device=local_rank)
+    eng.set_pilots(x, None)
+    eng.load_weights(nets)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+        if world > 1:       # the one collective of the path: all-gather of H-hat planes
+            dist.all_gather_into_tensor(gathered[0], Hr)
+            dist.all_gather_into_tensor(gathered[1], Hi)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+
+    # ---- timed region 1: device-resident (value) + live per-kernel-class profile
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.stats()["kernel_launches"]
+    eng.profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_end()
+    clocks = sampler.stop()
+    launches = eng.stats()["kernel_launches"] - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * npkt / (ms_step * 1e-3)
+
+    # compute-only (no all-gather) for N > 1, reported beside value
+    value_compute_only = None
+    if world > 1:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_compute_only = world * npkt / (float(t.item()) / args.steps * 1e-3)
+
+    # ---- timed region 2: end to end through the C ABI with pinned HOST buffers
+    def step_host():
+        eng.estimate_raw(Yh.data_ptr(), 0, npkt, 0, Hr_h.data_ptr(), Hi_h.data_ptr(), 0)
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()                      # synchronous: returns when H-hat is on the host
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * npkt / float(t.item())
+    checksum = float(Hr_h[:: max(1, rows // 64)].double().sum().item())    # device->host result actually read
+
+    # ---- roofline of the dominant kernel (FC layers on the tensor pipe), from the live profile
+    peaks, peak_src = measured_peaks()
+    fc_ms_per_step = prof["fc_ms"] / args.steps
+    ls_ms_per_step = prof["ls_ms"] / args.steps
+    fc_tflops = MLP_FLOP_PER_PKT * npkt / (fc_ms_per_step * 1e-3) / 1e12 if fc_ms_per_step > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "fc_tc_kernel" if args.precision != "fp32_simt" else "fc_simt_kernel",
+                "achieved": fc_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": fc_tflops / peaks["bf16_tflops"], "peak_source": peak_src + " bf16 burst (cuBLAS)",
+                "traffic": None, "avg_launch_ms": prof["fc_ms"] / max(1, prof["fc_launches"]),
+                "share_of_step": fc_ms_per_step / ms_step if ms_step > 0 else None,
+                "mma_passes": {"tf32x3": 3, "fp16x3": 3, "bf16x1": 1, "fp32_simt": 0}[args.precision]}
+    ls_gbs = LS_BYTES_PER_PKT * npkt / (ls_ms_per_step * 1e-3) / 1e9 if ls_ms_per_step > 0 else 0.0
+    roofline_ls = {"bound": "hbm", "kernel": "ls_kernel", "achieved": ls_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": ls_gbs / peaks["hbm_gbs"], "avg_launch_ms": prof["ls_ms"] / max(1, prof["ls_launches"]),
+                   "note": "algorithmic bytes = Y in + one operand-plane set out (2 MiB/packet)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, dt, cores = cpu_reference_run(args.cpu_sample, 1, 1)
+        cpu_baseline = {"value": val, "unit": "packets/s", "cores": cores, "kind": "port",
+                        "sample": "%d packets (torch-CPU c128 LS + fp32 FC, batch=Nt*Nr per predict), %.1f s" % (args.cpu_sample, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "channel-estimates/sec (32x4, 1024-sc pkts)", "value": value, "unit": "packets/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tf32x3": "tf32x3 split (fp32-grade), fp32 accumulate", "fp16x3": "fp16x3 split (fp32-grade), fp32 accumulate",
+                      "bf16x1": "bf16", "fp32_simt": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pkts_per_gpu": npkt, "precision": args.precision,
+                       "l2": "inputs (0.5 GiB Y) and outputs (0.5 GiB) per step exceed the 126 MB L2",
+                       "parallelism": "packets sharded over %d GPU(s)%s" % (world, ", all-gather of H planes in step" if world > 1 else "")},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
+                    "d2h_bytes_per_step": int(2 * rows * NSC * 4), "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_ls": roofline_ls,
+            "pair_estimates_per_s": value * NT * NR, "us_per_packet": 1e6 / value,
+        }
+        if value_compute_only is not None:
+            line["value_compute_only"] = value_compute_only
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MAMIMO_BENCH_PRECISION", "tf32x3"),
+                    choices=["tf32x3", "fp16x3", "bf16x1", "fp32_simt"])
+    ap.add_argument("--npkt", type=int, default=500)
+    ap.add_argument("--gen-pkts", type=int, default=125, help="distinct synthetic packets generated (tiled to npkt)")
+    ap.add_argument("--max-pkts", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "mamimo_b200_synth", os.path.join(ROOT, "dl-channel-estimation-mamimo_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["mamimo_b200_synth"] = mod
+    spec.loader.exec_module(mod)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,856 @@
+// C-ABI implementation (include/mamimo.h) of the channel-estimation engine.
+// Host side only orchestrates: tables, BN folding + operand splitting of the weights,
+// workspace, tensor maps, launches and the chunked host<->device pipeline.  All math on the
+// hot path runs in the kernels of ls.cuh / fc.cuh.
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mamimo.h"
+#include "fc.cuh"
+#include "ls.cuh"
+#include "tables.h"
+
+using namespace mm;
+
+namespace {
+
+struct HostLayer {
+  int in = 0, out = 0;
+  bool loaded = false, has_bn = false;
+  std::vector<float> W, b, g, be, mu, var;   // W: Keras [in][out]
+};
+
+struct DevLayer {
+  Operand w;               // [planes][Npad][Kpad]
+  float* bias = nullptr;   // [N]
+  int N = 0, K = 0;
+  float w_scale = 1.f;
+  CUtensorMap tmap_b;
+  CUtensorMap tmap_a;      // A operand of this layer (net-specific buffer for layer 0)
+};
+
+thread_local std::string g_create_err;
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+struct mamimo_engine {
+  mamimo_config cfg;
+  std::string err;
+  int num_sms = 0;
+  int rows_per_pkt = 0;
+  int max_pkts = 0;
+  int rows_alloc = 0;           // plane stride (rows) of every activation operand
+  int n_pil = 0;
+  int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
+  int elem_bytes = 4, planes = 1, block_k = 32;
+  float act_scale = 1.f;
+  bool hadamard = false;
+  bool finalized = false;
+  std::vector<float> hP;        // [n_tx][n_ltf] complex interleaved
+  float2* dP = nullptr;
+  float2* d_inv_den = nullptr;
+  HostLayer hl[2][MAMIMO_MAX_HIDDEN + 1];
+  DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
+  Operand act_in[2];            // layer-0 A operand per net
+  Operand act_h[2];             // ping-pong hidden activations (shared by both nets)
+  uint32_t* d_flags = nullptr;
+  uint32_t* h_flags = nullptr;  // pinned
+  // host-memory pipeline
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  void* st_in[2] = {nullptr, nullptr};
+  size_t st_in_bytes = 0;
+  void* st_in2[2] = {nullptr, nullptr};   // second input plane (modes A/B)
+  size_t st_in2_bytes = 0;
+  float* st_hr[2] = {nullptr, nullptr};
+  float* st_hi[2] = {nullptr, nullptr};
+  size_t st_h_bytes = 0;
+  void* st_hls[2] = {nullptr, nullptr};
+  size_t st_hls_bytes = 0;
+  mamimo_stats stats;
+  // optional per-kernel-class device timing (mamimo_profile_begin/end)
+  struct ProfRec { cudaEvent_t a, b; int cls; };
+  std::vector<ProfRec> prof;
+  bool profiling = false;
+};
+
+namespace {
+
+mamimo_status fail(mamimo_engine* e, mamimo_status s, const std::string& msg) {
+  if (e) e->err = msg; else g_create_err = msg;
+  return s;
+}
+mamimo_status fail_cuda(mamimo_engine* e, cudaError_t ce, const char* what) {
+  return fail(e, MAMIMO_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+}
+#define CK(e, call)                                         \
+  do {                                                      \
+    cudaError_t ce_ = (call);                               \
+    if (ce_ != cudaSuccess) return fail_cuda(e, ce_, #call); \
+  } while (0)
+
+enum { kClsLs = 0, kClsFc = 1, kClsStage = 2 };
+// RAII event bracket around one launch (no-op unless profiling)
+struct ProfScope {
+  mamimo_engine* e; cudaStream_t st; int idx = -1;
+  ProfScope(mamimo_engine* e_, cudaStream_t st_, int cls) : e(e_), st(st_) {
+    if (!e->profiling) return;
+    mamimo_engine::ProfRec r; r.cls = cls;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    e->prof.push_back(r);
+    idx = static_cast<int>(e->prof.size()) - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, st); }
+};
+
+bool is_sylvester(const std::vector<float>& P, int n_tx, int n_ltf) {
+  if (n_tx != n_ltf || n_tx < 1 || n_tx > 64 || (n_tx & (n_tx - 1))) return false;
+  for (int j = 0; j < n_tx; ++j)
+    for (int n = 0; n < n_ltf; ++n) {
+      const float want = (__builtin_popcount(j & n) & 1) ? -1.f : 1.f;
+      if (P[2 * (j * n_ltf + n)] != want || P[2 * (j * n_ltf + n) + 1] != 0.f) return false;
+    }
+  return true;
+}
+
+mamimo_status alloc_operand(mamimo_engine* e, Operand& op, int planes, int rows_alloc, int kpad, int elem_bytes) {
+  op.planes = planes; op.rows_alloc = rows_alloc; op.kpad = kpad; op.elem_bytes = elem_bytes;
+  CK(e, cudaMalloc(&op.ptr, op.bytes()));
+  CK(e, cudaMemset(op.ptr, 0, op.bytes()));
+  return MAMIMO_OK;
+}
+
+mamimo_status make_map(mamimo_engine* e, CUtensorMap* map, const Operand& op, int kpad, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMapDataType dt;
+  switch (e->cfg.precision) {
+    case MAMIMO_PREC_TF32X3: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    case MAMIMO_PREC_FP16X3: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; break;
+    default: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+  }
+  // the buffer may be used with a smaller row pitch than it was allocated with (hidden sizes differ)
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kpad), static_cast<cuuint64_t>(op.planes) * op.rows_alloc};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kpad) * op.elem_bytes};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(e->block_k), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, op.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
+  return MAMIMO_OK;
+}
+
+constexpr int kTcBN = 256;
+
+template <int S>
+mamimo_status set_tc_attr(mamimo_engine* e) {
+  using Cfg = FcTcCfg<S, kTcBN>;
+  const int smem = Cfg::kStages * Cfg::kStageBytes + Cfg::kAuxBytes + 1024;
+  CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return MAMIMO_OK;
+}
+
+// ------------------------------------------------------------------ weight split + upload
+template <int S>
+mamimo_status upload_layer(mamimo_engine* e, DevLayer& d, const std::vector<double>& Wf /*[in][out]*/,
+                           const std::vector<double>& bf, int in, int out) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  const int kpad = round_up(in, Sch::kBlockK);
+  const int npad = round_up(out, 256);
+  d.N = out; d.K = kpad;
+  double wmax = 0;
+  for (double v : Wf) wmax = std::max(wmax, std::fabs(v));
+  d.w_scale = 1.f;
+  if (S == kFp16x3 && wmax > 0) {
+    int ex;
+    std::frexp(wmax, &ex);                 // wmax = f * 2^ex, f in [0.5,1)
+    d.w_scale = std::ldexp(1.0f, 13 - ex); // max |w| * scale in [2^12, 2^13)
+  }
+  std::vector<E> host(static_cast<size_t>(Sch::kPlanes) * npad * kpad);
+  memset(host.data(), 0, host.size() * sizeof(E));
+  bool ovf = false;
+  for (int n = 0; n < out; ++n)
+    for (int k = 0; k < in; ++k) {
+      E p[Sch::kPlanes];
+      Sch::split(static_cast<float>(Wf[static_cast<size_t>(k) * out + n]), d.w_scale, p, &ovf);
+      for (int q = 0; q < Sch::kPlanes; ++q) host[(static_cast<size_t>(q) * npad + n) * kpad + k] = p[q];
+    }
+  if (ovf) return fail(e, MAMIMO_ERR_RANGE, "weight split overflow");
+  d.w.planes = Sch::kPlanes; d.w.rows_alloc = npad; d.w.kpad = kpad; d.w.elem_bytes = sizeof(E);
+  CK(e, cudaMalloc(&d.w.ptr, d.w.bytes()));
+  CK(e, cudaMemcpy(d.w.ptr, host.data(), d.w.bytes(), cudaMemcpyHostToDevice));
+  std::vector<float> b32(out);
+  for (int n = 0; n < out; ++n) b32[n] = static_cast<float>(bf[n]);
+  CK(e, cudaMalloc(&d.bias, out * sizeof(float)));
+  CK(e, cudaMemcpy(d.bias, b32.data(), out * sizeof(float), cudaMemcpyHostToDevice));
+  return MAMIMO_OK;
+}
+
+// ------------------------------------------------------------------ launches
+template <int S, int NLTF, bool HAD>
+mamimo_status launch_ls_t(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+  const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
+  const long long grid = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
+  const size_t smem = (static_cast<size_t>(a.n_tx) * (a.pil_per_tile + 3) + (HAD ? 0 : a.n_tx * a.n_ltf)) * sizeof(float2);
+  if (smem > 48 * 1024)
+    CK(e, cudaFuncSetAttribute(ls_kernel<S, NLTF, HAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)));
+  {
+    ProfScope ps(e, st, kClsLs);
+    ls_kernel<S, NLTF, HAD><<<static_cast<unsigned>(grid), 128, smem, st>>>(a);
+  }
+  CK(e, cudaGetLastError());
+  e->stats.kernel_launches++;
+  return MAMIMO_OK;
+}
+
+template <int S>
+mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+#define LS_CASE(n)                                                    \
+  case n:                                                             \
+    return e->hadamard ? launch_ls_t<S, n, true>(e, a, st) : launch_ls_t<S, n, false>(e, a, st);
+  switch (a.n_ltf) {
+    LS_CASE(1) LS_CASE(2) LS_CASE(4) LS_CASE(8) LS_CASE(16) LS_CASE(32) LS_CASE(64)
+    default: return launch_ls_t<S, 0, false>(e, a, st);
+  }
+#undef LS_CASE
+}
+
+template <int S>
+mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStream_t st) {
+  ProfScope ps(e, st, kClsFc);
+  if constexpr (S == kFp32Simt) {
+    const int grid = ((a.M + 127) / 128) * ((a.N + 127) / 128);
+    fc_simt_kernel<S><<<grid, 256, 0, st>>>(a);
+  } else {
+    using Cfg = FcTcCfg<S, kTcBN>;
+    const int tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcBN - 1) / kTcBN);
+    const int grid = std::min(tiles, e->num_sms);
+    const int smem = Cfg::kStages * Cfg::kStageBytes + Cfg::kAuxBytes + 1024;
+    fc_tc_kernel<S, kTcBN><<<grid, kFcThreads, smem, st>>>(d.tmap_a, d.tmap_b, a);
+  }
+  CK(e, cudaGetLastError());
+  e->stats.kernel_launches++;
+  return MAMIMO_OK;
+}
+
+// all FC layers of both nets for n_rows rows already staged in act_in[0/1]
+template <int S>
+mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, cudaStream_t st) {
+  for (int net = 0; net < 2; ++net) {
+    for (int l = 0; l < e->n_layers; ++l) {
+      const DevLayer& d = e->dl[net][l];
+      const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
+      const bool last = (l == e->n_layers - 1);
+      FcArgs a;
+      memset(&a, 0, sizeof(a));
+      a.M = n_rows; a.N = d.N; a.num_k_blocks = d.K / e->block_k;
+      a.a_plane_rows = A.rows_alloc; a.b_plane_rows = d.w.rows_alloc;
+      a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = last ? 0 : 1;
+      a.flags = e->d_flags;
+      a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
+      if (last) {
+        a.out_f32 = net == 0 ? out_r : out_i;
+        a.out_ld = d.N;
+      } else {
+        const Operand& O = e->act_h[l & 1];
+        a.out_planes = O.ptr; a.out_kpad = e->dl[net][l + 1].K; a.out_plane_rows = O.rows_alloc;
+        a.out_scale = e->act_scale;
+      }
+      mamimo_status s = launch_fc<S>(e, d, a, st);
+      if (s != MAMIMO_OK) return s;
+    }
+  }
+  return MAMIMO_OK;
+}
+
+template <int S>
+mamimo_status run_ls(mamimo_engine* e, const void* dY, int y_double, int n_pkt, void* dHls, int h_double,
+                     bool want_planes, cudaStream_t st) {
+  LsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Y = dY; a.P = e->dP; a.inv_den = e->d_inv_den; a.H_ls = dHls;
+  if (want_planes) {
+    a.planes[0] = e->act_in[0].ptr; a.planes[1] = e->act_in[1].ptr;
+    a.plane_rows = e->act_in[0].rows_alloc; a.kpad = e->act_in[0].kpad;
+  }
+  a.scale = e->act_scale;
+  a.n_pkt = n_pkt; a.n_rx = e->cfg.n_rx; a.n_tx = e->cfg.n_tx; a.n_ltf = e->cfg.n_ltf;
+  a.n_sc = e->cfg.n_sc; a.n_ps = e->cfg.n_ps; a.n_pil = e->n_pil;
+  a.pil_per_tile = std::max(1, 128 / e->cfg.n_ps);
+  a.y_double = y_double; a.h_double = h_double; a.flags = e->d_flags;
+  return launch_ls<S>(e, a, st);
+}
+
+template <int S>
+mamimo_status run_stage_planes(mamimo_engine* e, const float* dXr, const float* dXi, int64_t rows, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t total = rows * e->cfg.d_in;
+  const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
+  for (int net = 0; net < 2; ++net) {
+    const Operand& A = e->act_in[net];
+    ProfScope ps(e, st, kClsStage);
+    stage_planes_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dXr : dXi, A.ptr, rows, e->cfg.d_in, A.rows_alloc,
+                                                     A.kpad, e->act_scale, e->d_flags);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  return MAMIMO_OK;
+}
+
+template <int S>
+mamimo_status run_stage_time(mamimo_engine* e, const float* dSr, const float* dSi, int64_t n_pkt, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t n_prx = n_pkt * e->cfg.n_rx;
+  const int64_t total = n_prx * e->cfg.n_tx * e->cfg.d_in;
+  const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
+  for (int net = 0; net < 2; ++net) {
+    const Operand& A = e->act_in[net];
+    ProfScope ps(e, st, kClsStage);
+    stage_time_p_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dSr : dSi, e->dP, A.ptr, n_prx, e->cfg.n_tx,
+                                                     e->cfg.n_ltf, e->cfg.len_ltf, A.rows_alloc, A.kpad,
+                                                     e->act_scale, e->d_flags);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  return MAMIMO_OK;
+}
+
+#define DISPATCH_S(e, expr)                                               \
+  [&]() -> mamimo_status {                                                \
+    switch ((e)->cfg.precision) {                                         \
+      case MAMIMO_PREC_FP32_SIMT: { constexpr int S = kFp32Simt; return expr; } \
+      case MAMIMO_PREC_TF32X3: { constexpr int S = kTf32x3; return expr; }      \
+      case MAMIMO_PREC_FP16X3: { constexpr int S = kFp16x3; return expr; }      \
+      case MAMIMO_PREC_BF16X1: { constexpr int S = kBf16x1; return expr; }      \
+      default: return fail(e, MAMIMO_ERR_INVALID, "bad precision");      \
+    }                                                                     \
+  }()
+
+mamimo_status check_flags(mamimo_engine* e, cudaStream_t st) {
+  CK(e, cudaMemcpyAsync(e->h_flags, e->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CK(e, cudaStreamSynchronize(st));
+  const uint32_t f = *e->h_flags;
+  e->stats.last_device_flags = f;
+  if (f) {
+    CK(e, cudaMemsetAsync(e->d_flags, 0, sizeof(uint32_t), st));
+    if (f & kFlagTimeout) return fail(e, MAMIMO_ERR_TIMEOUT, "device pipeline wait timed out (kernel aborted)");
+    if (f & kFlagRange) return fail(e, MAMIMO_ERR_RANGE, "fp16 split operand overflow: lower act_scale_log2 or use TF32X3");
+  }
+  return MAMIMO_OK;
+}
+
+mamimo_status ensure_staging(mamimo_engine* e, size_t in_bytes, size_t in2_bytes, size_t h_bytes, size_t hls_bytes) {
+  for (int i = 0; i < 2; ++i) {
+    if (in_bytes > e->st_in_bytes) { if (e->st_in[i]) cudaFree(e->st_in[i]); CK(e, cudaMalloc(&e->st_in[i], in_bytes)); }
+    if (in2_bytes > e->st_in2_bytes) { if (e->st_in2[i]) cudaFree(e->st_in2[i]); CK(e, cudaMalloc(&e->st_in2[i], in2_bytes)); }
+    if (h_bytes > e->st_h_bytes) {
+      if (e->st_hr[i]) cudaFree(e->st_hr[i]);
+      if (e->st_hi[i]) cudaFree(e->st_hi[i]);
+      CK(e, cudaMalloc(&e->st_hr[i], h_bytes));
+      CK(e, cudaMalloc(&e->st_hi[i], h_bytes));
+    }
+    if (hls_bytes > e->st_hls_bytes) { if (e->st_hls[i]) cudaFree(e->st_hls[i]); CK(e, cudaMalloc(&e->st_hls[i], hls_bytes)); }
+  }
+  e->st_in_bytes = std::max(e->st_in_bytes, in_bytes);
+  e->st_in2_bytes = std::max(e->st_in2_bytes, in2_bytes);
+  e->st_h_bytes = std::max(e->st_h_bytes, h_bytes);
+  e->st_hls_bytes = std::max(e->st_hls_bytes, hls_bytes);
+  return MAMIMO_OK;
+}
+
+// Generic chunked runner.  `units` are packets (modes A/C) or rows (mode B).
+//   stage(chunk_units, in0, in1, hls, hr, hi, stream): enqueue kernels for one device-resident chunk
+template <class StageFn>
+mamimo_status run_chunked(mamimo_engine* e, int64_t n_units, int64_t units_per_chunk, const void* in0,
+                          size_t in0_unit_bytes, const void* in1, size_t in1_unit_bytes, void* hls,
+                          size_t hls_unit_bytes, float* hr, float* hi, size_t h_unit_bytes, mamimo_mem mem,
+                          cudaStream_t user_stream, StageFn stage) {
+  if (n_units == 0) return MAMIMO_OK;
+  if (mem == MAMIMO_MEM_DEVICE) {
+    for (int64_t u0 = 0; u0 < n_units; u0 += units_per_chunk) {
+      const int64_t n = std::min(units_per_chunk, n_units - u0);
+      mamimo_status s = stage(n, static_cast<const char*>(in0) + u0 * in0_unit_bytes,
+                              in1 ? static_cast<const char*>(in1) + u0 * in1_unit_bytes : nullptr,
+                              hls ? static_cast<char*>(hls) + u0 * hls_unit_bytes : nullptr,
+                              hr ? reinterpret_cast<float*>(reinterpret_cast<char*>(hr) + u0 * h_unit_bytes) : nullptr,
+                              hi ? reinterpret_cast<float*>(reinterpret_cast<char*>(hi) + u0 * h_unit_bytes) : nullptr,
+                              user_stream);
+      if (s != MAMIMO_OK) return s;
+    }
+    return MAMIMO_OK;
+  }
+  // host buffers: double-buffered H2D -> compute -> D2H on three streams
+  const int64_t cu = std::min(units_per_chunk, n_units);
+  mamimo_status s = ensure_staging(e, cu * in0_unit_bytes, in1 ? cu * in1_unit_bytes : 0, hr ? cu * h_unit_bytes : 0,
+                                   hls ? cu * hls_unit_bytes : 0);
+  if (s != MAMIMO_OK) return s;
+  int64_t c = 0;
+  for (int64_t u0 = 0; u0 < n_units; u0 += units_per_chunk, ++c) {
+    const int b = static_cast<int>(c & 1);
+    const int64_t n = std::min(units_per_chunk, n_units - u0);
+    if (c >= 2) {
+      CK(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));   // previous user of st_in[b] has consumed it
+      CK(e, cudaStreamWaitEvent(e->s_comp, e->ev_out[b], 0));   // previous outputs in st_h*[b] are on the host
+    }
+    CK(e, cudaMemcpyAsync(e->st_in[b], static_cast<const char*>(in0) + u0 * in0_unit_bytes, n * in0_unit_bytes,
+                          cudaMemcpyHostToDevice, e->s_h2d));
+    e->stats.h2d_bytes += n * in0_unit_bytes;
+    if (in1) {
+      CK(e, cudaMemcpyAsync(e->st_in2[b], static_cast<const char*>(in1) + u0 * in1_unit_bytes, n * in1_unit_bytes,
+                            cudaMemcpyHostToDevice, e->s_h2d));
+      e->stats.h2d_bytes += n * in1_unit_bytes;
+    }
+    CK(e, cudaEventRecord(e->ev_in[b], e->s_h2d));
+    CK(e, cudaStreamWaitEvent(e->s_comp, e->ev_in[b], 0));
+    s = stage(n, e->st_in[b], in1 ? e->st_in2[b] : nullptr, hls ? e->st_hls[b] : nullptr, hr ? e->st_hr[b] : nullptr,
+              hi ? e->st_hi[b] : nullptr, e->s_comp);
+    if (s != MAMIMO_OK) return s;
+    CK(e, cudaEventRecord(e->ev_comp[b], e->s_comp));
+    CK(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
+    if (hls) {
+      CK(e, cudaMemcpyAsync(static_cast<char*>(hls) + u0 * hls_unit_bytes, e->st_hls[b], n * hls_unit_bytes,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+      e->stats.d2h_bytes += n * hls_unit_bytes;
+    }
+    if (hr) {
+      CK(e, cudaMemcpyAsync(reinterpret_cast<char*>(hr) + u0 * h_unit_bytes, e->st_hr[b], n * h_unit_bytes,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+      CK(e, cudaMemcpyAsync(reinterpret_cast<char*>(hi) + u0 * h_unit_bytes, e->st_hi[b], n * h_unit_bytes,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+      e->stats.d2h_bytes += 2 * n * h_unit_bytes;
+    }
+    CK(e, cudaEventRecord(e->ev_out[b], e->s_d2h));
+  }
+  CK(e, cudaStreamSynchronize(e->s_d2h));
+  return check_flags(e, e->s_comp);
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int32_t mamimo_abi_version(void) { return MAMIMO_ABI_VERSION; }
+
+const char* mamimo_status_string(mamimo_status s) {
+  switch (s) {
+    case MAMIMO_OK: return "ok";
+    case MAMIMO_ERR_INVALID: return "invalid argument";
+    case MAMIMO_ERR_CUDA: return "CUDA error";
+    case MAMIMO_ERR_NOMEM: return "out of memory";
+    case MAMIMO_ERR_STATE: return "invalid engine state";
+    case MAMIMO_ERR_UNSUPPORTED: return "unsupported device or configuration";
+    case MAMIMO_ERR_RANGE: return "operand range overflow";
+    case MAMIMO_ERR_TIMEOUT: return "device pipeline timeout";
+  }
+  return "unknown";
+}
+
+const char* mamimo_last_error(const mamimo_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+void mamimo_config_init(mamimo_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = MAMIMO_ABI_VERSION;
+  c->n_ps = 1;
+  c->precision = MAMIMO_PREC_TF32X3;
+  c->input_mode = MAMIMO_INPUT_LS;
+  c->act_scale_log2 = 6;
+}
+
+void mamimo_vht_ltf256(int8_t out[256]) {
+  for (int i = 0; i < 256; ++i) out[i] = kVhtLtf256[i] == '+' ? 1 : (kVhtLtf256[i] == '-' ? -1 : 0);
+}
+
+int32_t mamimo_carriers_locations(int32_t* out, int32_t capacity) {
+  int32_t n = 0;
+  for (int i = 1; i <= kFftLen; ++i) {
+    if (is_null_carrier(i) || is_pilot_carrier(i)) continue;
+    if (out && n < capacity) out[n] = i;
+    ++n;
+  }
+  return n;
+}
+
+mamimo_status mamimo_default_p(int32_t n, float* out) {
+  if (n < 1 || (n & (n - 1)) || !out) return MAMIMO_ERR_INVALID;
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < n; ++k) out[j * n + k] = (__builtin_popcount(j & k) & 1) ? -1.f : 1.f;
+  return MAMIMO_OK;
+}
+
+int64_t mamimo_pair_row(int64_t p, int32_t i_rx, int32_t i_tx, int32_t n_rx, int32_t n_tx) {
+  return p * (static_cast<int64_t>(n_rx) * n_tx) + static_cast<int64_t>(i_rx) * n_tx + i_tx;
+}
+
+void* mamimo_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void mamimo_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
+  if (!cfg || !out) return fail(nullptr, MAMIMO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MAMIMO_ABI_VERSION) return fail(nullptr, MAMIMO_ERR_INVALID, "abi_version mismatch");
+  if (cfg->n_tx < 1 || cfg->n_rx < 1 || cfg->n_ltf < 1 || cfg->n_sc < 1 || cfg->n_ps < 1)
+    return fail(nullptr, MAMIMO_ERR_INVALID, "n_tx, n_rx, n_ltf, n_sc, n_ps must be >= 1");
+  if (cfg->n_ltf > 64 || cfg->n_tx > 64) return fail(nullptr, MAMIMO_ERR_INVALID, "n_tx and n_ltf are limited to 64");
+  if (cfg->n_hidden < 0 || cfg->n_hidden > MAMIMO_MAX_HIDDEN) return fail(nullptr, MAMIMO_ERR_INVALID, "n_hidden out of range");
+  if (cfg->precision < 0 || cfg->precision > MAMIMO_PREC_BF16X1) return fail(nullptr, MAMIMO_ERR_INVALID, "bad precision");
+  if (cfg->input_mode < 0 || cfg->input_mode > MAMIMO_INPUT_TIME_P) return fail(nullptr, MAMIMO_ERR_INVALID, "bad input_mode");
+  const bool has_mlp = cfg->d_out > 0;
+  if (has_mlp) {
+    if (cfg->d_in < 1) return fail(nullptr, MAMIMO_ERR_INVALID, "d_in must be >= 1");
+    for (int i = 0; i < cfg->n_hidden; ++i)
+      if (cfg->hidden[i] < 1) return fail(nullptr, MAMIMO_ERR_INVALID, "hidden sizes must be >= 1");
+    if (cfg->input_mode == MAMIMO_INPUT_LS && cfg->d_in != cfg->n_sc)
+      return fail(nullptr, MAMIMO_ERR_INVALID, "mode C needs d_in == n_sc");
+    if (cfg->input_mode == MAMIMO_INPUT_TIME_P && (cfg->len_ltf < 1 || cfg->d_in != cfg->len_ltf + cfg->n_tx || cfg->n_ltf != cfg->n_tx))
+      return fail(nullptr, MAMIMO_ERR_INVALID, "mode A needs d_in == len_ltf + n_tx and n_ltf == n_tx");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, MAMIMO_ERR_UNSUPPORTED, "no CUDA device: this engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MAMIMO_ERR_INVALID, "bad device ordinal");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, MAMIMO_ERR_CUDA, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, MAMIMO_ERR_UNSUPPORTED, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+
+  mamimo_engine* e = new mamimo_engine();
+  e->cfg = *cfg;
+  memset(&e->stats, 0, sizeof(e->stats));
+  e->num_sms = prop.multiProcessorCount;
+  e->rows_per_pkt = cfg->n_tx * cfg->n_rx;
+  e->n_pil = (cfg->n_sc + cfg->n_ps - 1) / cfg->n_ps;
+  e->n_layers = has_mlp ? cfg->n_hidden + 1 : 0;
+  mamimo_status s = MAMIMO_OK;
+  auto bail = [&](mamimo_status st) { g_create_err = e->err; mamimo_destroy(e); return st; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return bail(MAMIMO_ERR_CUDA); }
+
+  switch (cfg->precision) {
+    case MAMIMO_PREC_FP32_SIMT: e->elem_bytes = 4; e->planes = 1; e->block_k = Scheme<kFp32Simt>::kBlockK; break;
+    case MAMIMO_PREC_TF32X3: e->elem_bytes = 4; e->planes = 2; e->block_k = Scheme<kTf32x3>::kBlockK; break;
+    case MAMIMO_PREC_FP16X3: e->elem_bytes = 2; e->planes = 2; e->block_k = Scheme<kFp16x3>::kBlockK; break;
+    default: e->elem_bytes = 2; e->planes = 1; e->block_k = Scheme<kBf16x1>::kBlockK; break;
+  }
+  e->act_scale = (cfg->precision == MAMIMO_PREC_FP16X3)
+                     ? std::ldexp(1.0f, cfg->act_scale_log2 ? cfg->act_scale_log2 : 6) : 1.0f;
+
+  // chunking: ~64K rows per chunk by default
+  int rows_per_unit = cfg->input_mode == MAMIMO_INPUT_PLANES ? 1 : e->rows_per_pkt;
+  e->max_pkts = cfg->max_pkts > 0 ? cfg->max_pkts : std::max(1, 65536 / rows_per_unit);
+  const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
+  if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }
+  e->rows_alloc = round_up(static_cast<int>(rows), 128);
+
+  auto ck = [&](cudaError_t ce, const char* what) { if (ce != cudaSuccess && s == MAMIMO_OK) s = fail_cuda(e, ce, what); };
+  ck(cudaMalloc(&e->d_flags, sizeof(uint32_t)), "cudaMalloc flags");
+  if (s == MAMIMO_OK) ck(cudaMemset(e->d_flags, 0, sizeof(uint32_t)), "memset flags");
+  ck(cudaMallocHost(&e->h_flags, sizeof(uint32_t)), "cudaMallocHost flags");
+  ck(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), "stream");
+  ck(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), "stream");
+  ck(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), "stream");
+  for (int i = 0; i < 2; ++i) {
+    ck(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming), "event");
+    ck(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming), "event");
+    ck(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming), "event");
+  }
+  if (s != MAMIMO_OK) return bail(s);
+
+  if (has_mlp) {
+    const int kin = round_up(cfg->d_in, e->block_k);
+    int kh = e->block_k;
+    for (int i = 0; i < cfg->n_hidden; ++i) kh = std::max(kh, round_up(cfg->hidden[i], e->block_k));
+    for (int net = 0; net < 2 && s == MAMIMO_OK; ++net) s = alloc_operand(e, e->act_in[net], e->planes, e->rows_alloc, kin, e->elem_bytes);
+    if (cfg->n_hidden > 0)
+      for (int i = 0; i < (cfg->n_hidden > 1 ? 2 : 1) && s == MAMIMO_OK; ++i)
+        s = alloc_operand(e, e->act_h[i], e->planes, e->rows_alloc, kh, e->elem_bytes);
+    if (s != MAMIMO_OK) return bail(s);
+    int in = cfg->d_in;
+    for (int l = 0; l <= cfg->n_hidden; ++l) {
+      const int outw = l < cfg->n_hidden ? cfg->hidden[l] : cfg->d_out;
+      for (int net = 0; net < 2; ++net) { e->hl[net][l].in = in; e->hl[net][l].out = outw; }
+      in = outw;
+    }
+    if (cfg->precision == MAMIMO_PREC_TF32X3) s = set_tc_attr<kTf32x3>(e);
+    else if (cfg->precision == MAMIMO_PREC_FP16X3) s = set_tc_attr<kFp16x3>(e);
+    else if (cfg->precision == MAMIMO_PREC_BF16X1) s = set_tc_attr<kBf16x1>(e);
+    if (s != MAMIMO_OK) return bail(s);
+  }
+  // default tables (all-ones pilots, Sylvester-Hadamard P) when a default P exists for this shape
+  if ((cfg->n_tx == cfg->n_ltf && (cfg->n_tx & (cfg->n_tx - 1)) == 0) || cfg->n_ltf == 1) {
+    s = mamimo_set_pilots(e, nullptr, nullptr);
+    if (s != MAMIMO_OK) return bail(s);
+  }
+  *out = e;
+  return MAMIMO_OK;
+}
+
+void mamimo_destroy(mamimo_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags);
+  if (e->h_flags) cudaFreeHost(e->h_flags);
+  for (int net = 0; net < 2; ++net) {
+    fr(e->act_in[net].ptr);
+    for (int l = 0; l <= MAMIMO_MAX_HIDDEN; ++l) { fr(e->dl[net][l].w.ptr); fr(e->dl[net][l].bias); }
+  }
+  for (int i = 0; i < 2; ++i) {
+    fr(e->act_h[i].ptr); fr(e->st_in[i]); fr(e->st_in2[i]); fr(e->st_hr[i]); fr(e->st_hi[i]); fr(e->st_hls[i]);
+    if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+    if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+    if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+  }
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_comp) cudaStreamDestroy(e->s_comp);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  delete e;
+}
+
+mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  CK(e, cudaSetDevice(e->cfg.device));
+  const int nt = e->cfg.n_tx, nl = e->cfg.n_ltf;
+  e->hP.assign(static_cast<size_t>(2) * nt * nl, 0.f);
+  if (P) {
+    memcpy(e->hP.data(), P, e->hP.size() * sizeof(float));
+  } else {
+    if (nt == nl && (nt & (nt - 1)) == 0) {
+      for (int j = 0; j < nt; ++j)
+        for (int n = 0; n < nl; ++n) e->hP[2 * (j * nl + n)] = (__builtin_popcount(j & n) & 1) ? -1.f : 1.f;
+    } else if (nl == 1) {
+      for (int j = 0; j < nt; ++j) e->hP[2 * j] = 1.f;
+    } else {
+      return fail(e, MAMIMO_ERR_INVALID, "no default P for this (n_tx, n_ltf): pass P explicitly");
+    }
+  }
+  e->hadamard = is_sylvester(e->hP, nt, nl);
+  std::vector<float> inv(static_cast<size_t>(2) * e->n_pil);
+  for (int i = 0; i < e->n_pil; ++i) {
+    const double xr = x_pilot ? x_pilot[2 * i] : 1.0, xi = x_pilot ? x_pilot[2 * i + 1] : 0.0;
+    const double den = (xr * xr + xi * xi) * nl;
+    if (den == 0.0) return fail(e, MAMIMO_ERR_INVALID, "pilot tone " + std::to_string(i) + " is zero");
+    inv[2 * i] = static_cast<float>(xr / den);          // 1/(nl*x) = conj(x)/(nl*|x|^2)
+    inv[2 * i + 1] = static_cast<float>(-xi / den);
+  }
+  if (!e->dP) CK(e, cudaMalloc(&e->dP, e->hP.size() * sizeof(float)));
+  if (!e->d_inv_den) CK(e, cudaMalloc(&e->d_inv_den, inv.size() * sizeof(float)));
+  CK(e, cudaMemcpy(e->dP, e->hP.data(), e->hP.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(e, cudaMemcpy(e->d_inv_den, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_load_layer(mamimo_engine* e, int32_t net, int32_t layer, const float* W, const float* b,
+                                const float* g, const float* be, const float* mu, const float* var) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (e->n_layers == 0) return fail(e, MAMIMO_ERR_STATE, "engine was created without an MLP (d_out == 0)");
+  if (net < 0 || net > 1 || layer < 0 || layer >= e->n_layers || !W || !b) return fail(e, MAMIMO_ERR_INVALID, "bad net/layer/pointer");
+  const bool bn = g || be || mu || var;
+  if (bn && !(g && be && mu && var)) return fail(e, MAMIMO_ERR_INVALID, "BN needs gamma, beta, mean and var");
+  if (bn && layer == e->n_layers - 1) return fail(e, MAMIMO_ERR_INVALID, "the final linear layer has no BatchNormalization");
+  HostLayer& L = e->hl[net][layer];
+  L.W.assign(W, W + static_cast<size_t>(L.in) * L.out);
+  L.b.assign(b, b + L.out);
+  L.has_bn = bn;
+  if (bn) { L.g.assign(g, g + L.out); L.be.assign(be, be + L.out); L.mu.assign(mu, mu + L.out); L.var.assign(var, var + L.out); }
+  L.loaded = true;
+  e->finalized = false;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (e->n_layers == 0) return fail(e, MAMIMO_ERR_STATE, "no MLP configured");
+  CK(e, cudaSetDevice(e->cfg.device));
+  for (int net = 0; net < 2; ++net)
+    for (int l = 0; l < e->n_layers; ++l)
+      if (!e->hl[net][l].loaded) return fail(e, MAMIMO_ERR_STATE, "layer " + std::to_string(l) + " of net " + std::to_string(net) + " not loaded");
+  for (int net = 0; net < 2; ++net) {
+    std::vector<double> scale, shift;   // BN of the previous layer (ReLU precedes BN: folds forward)
+    for (int l = 0; l < e->n_layers; ++l) {
+      const HostLayer& L = e->hl[net][l];
+      std::vector<double> Wf(static_cast<size_t>(L.in) * L.out), bf(L.out);
+      for (int n = 0; n < L.out; ++n) bf[n] = L.b[n];
+      for (int k = 0; k < L.in; ++k)
+        for (int n = 0; n < L.out; ++n) {
+          const double w = L.W[static_cast<size_t>(k) * L.out + n];
+          if (!scale.empty()) {
+            bf[n] += shift[k] * w;
+            Wf[static_cast<size_t>(k) * L.out + n] = scale[k] * w;
+          } else {
+            Wf[static_cast<size_t>(k) * L.out + n] = w;
+          }
+        }
+      scale.clear(); shift.clear();
+      if (L.has_bn) {
+        scale.resize(L.out); shift.resize(L.out);
+        for (int n = 0; n < L.out; ++n) {
+          scale[n] = L.g[n] / std::sqrt(static_cast<double>(L.var[n]) + 1e-3);   // Keras BN epsilon
+          shift[n] = L.be[n] - L.mu[n] * scale[n];
+        }
+      }
+      DevLayer& d = e->dl[net][l];
+      if (d.w.ptr) { cudaFree(d.w.ptr); d.w.ptr = nullptr; }
+      if (d.bias) { cudaFree(d.bias); d.bias = nullptr; }
+      mamimo_status s = DISPATCH_S(e, (upload_layer<S>(e, d, Wf, bf, L.in, L.out)));
+      if (s != MAMIMO_OK) return s;
+      if (e->cfg.precision != MAMIMO_PREC_FP32_SIMT) {
+        s = make_map(e, &d.tmap_b, d.w, d.w.kpad, kTcBN);
+        if (s != MAMIMO_OK) return s;
+        const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
+        s = make_map(e, &d.tmap_a, A, d.K, kFcBlockM);
+        if (s != MAMIMO_OK) return s;
+      }
+    }
+  }
+  e->finalized = true;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type, mamimo_mem y_mem,
+                                 int64_t n_pkt, void* H_ls, mamimo_ctype h_type, mamimo_mem h_mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (n_pkt < 0 || (n_pkt > 0 && (!Y || !H_ls))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
+  if (y_mem != h_mem) return fail(e, MAMIMO_ERR_INVALID, "Y and H_ls must live in the same memory kind");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
+  const size_t hb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_tx * e->cfg.n_sc * (h_type == MAMIMO_C128 ? 16 : 8);
+  auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float*, float*, cudaStream_t st) {
+    return DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, h_type == MAMIMO_C128, false, st)));
+  };
+  return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hb, nullptr, nullptr, 0, y_mem,
+                     static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type, int64_t n_pkt, void* H_ls,
+                              float* H_real, float* H_imag, mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (e->cfg.input_mode != MAMIMO_INPUT_LS) return fail(e, MAMIMO_ERR_STATE, "engine not configured for mode C (INPUT_LS)");
+  if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
+  if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
+  if (n_pkt < 0 || (n_pkt > 0 && (!Y || !H_real || !H_imag))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
+  const size_t hlsb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.n_sc * 8;
+  const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
+  auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
+    mamimo_status s = DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, 0, true, st)));
+    if (s != MAMIMO_OK) return s;
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+  };
+  return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem,
+                     static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const float* X_imag, int64_t n_rows,
+                                    float* Y_real, float* Y_imag, mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (e->cfg.input_mode != MAMIMO_INPUT_PLANES) return fail(e, MAMIMO_ERR_STATE, "engine not configured for mode B (INPUT_PLANES)");
+  if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
+  if (n_rows < 0 || (n_rows > 0 && (!X_real || !X_imag || !Y_real || !Y_imag))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t xb = static_cast<size_t>(e->cfg.d_in) * sizeof(float);
+  const size_t hb = static_cast<size_t>(e->cfg.d_out) * sizeof(float);
+  auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
+    mamimo_status s = DISPATCH_S(e, (run_stage_planes<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
+    if (s != MAMIMO_OK) return s;
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n), hr, hi, st)));
+  };
+  return run_chunked(e, n_rows, e->max_pkts, X_real, xb, X_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
+                     static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const float* sig_imag, int64_t n_pkt,
+                                  float* Y_real, float* Y_imag, mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (e->cfg.input_mode != MAMIMO_INPUT_TIME_P) return fail(e, MAMIMO_ERR_STATE, "engine not configured for mode A (INPUT_TIME_P)");
+  if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
+  if (n_pkt < 0 || (n_pkt > 0 && (!sig_real || !sig_imag || !Y_real || !Y_imag))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t xb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.len_ltf * sizeof(float);
+  const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
+  auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
+    mamimo_status s = DISPATCH_S(e, (run_stage_time<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
+    if (s != MAMIMO_OK) return s;
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+  };
+  return run_chunked(e, n_pkt, e->max_pkts, sig_real, xb, sig_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
+                     static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_synchronize(mamimo_engine* e) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaDeviceSynchronize());
+  return check_flags(e, e->s_comp);
+}
+
+mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out) {
+  if (!e || !out) return MAMIMO_ERR_INVALID;
+  *out = e->stats;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_profile_begin(mamimo_engine* e) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->profiling = true;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_profile_end(mamimo_engine* e, mamimo_profile* out) {
+  if (!e || !out) return MAMIMO_ERR_INVALID;
+  e->profiling = false;
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (r.cls == kClsLs) { out->ls_ms += ms; out->ls_launches++; }
+      else if (r.cls == kClsFc) { out->fc_ms += ms; out->fc_launches++; }
+      else { out->stage_ms += ms; out->stage_launches++; }
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  e->prof.clear();
+  return MAMIMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// FC (Dense) layer kernels:  D[m][n] = act( alpha * sum_k A[m][k] W[n][k] + bias[n] )
+//
+// Replaces the Keras Dense(+relu) / Dense(linear) layers of the reference's CSI predictor
+// (massiveMIMO_CSI_prediction_DNN.py:211-227); BatchNormalization is folded into the next
+// layer's W/bias on the host (engine.cu), Dropout is the identity at inference.
+//
+//   fc_tc_kernel   -- tcgen05 + TMEM + TMA, warp-specialised, persistent over output tiles.
+//                     Split-precision operands (schemes.cuh): 3 UMMA passes per k-step
+//                     accumulate hi.hi + hi.lo + lo.hi in FP32 in tensor memory.
+//   fc_simt_kernel -- exact-FP32 CUDA-core GEMM: the on-device accuracy anchor
+//                     (MAMIMO_PREC_FP32_SIMT), also usable when 1e-7-grade agreement is wanted.
+//
+// Both K-major: A = activations [rows][Kpad], W = weights [N][Kpad] (the transpose of the
+// Keras kernel), so each output element is a dot product of two contiguous rows.
+#pragma once
+#include "ptx.cuh"
+#include "schemes.cuh"
+
+namespace mm {
+
+struct FcArgs {
+  int M;                 // valid rows
+  int N;                 // valid output features
+  int num_k_blocks;      // Kpad / kBlockK
+  int a_plane_rows;      // rows_alloc of the A operand (plane stride, rows)
+  int b_plane_rows;      // Npad of the W operand
+  const float* bias;     // [N], BN-folded
+  float alpha;           // undoes the operand scales: 1 / (a_scale * w_scale)
+  int relu;
+  // hidden layer: next layer's A operand (split planes).  nullptr for the final layer
+  void* out_planes;
+  int out_kpad;
+  int out_plane_rows;
+  float out_scale;
+  // final layer: float32 [M][out_ld]
+  float* out_f32;
+  int out_ld;
+  uint32_t* flags;
+  // SIMT kernel only (the tcgen05 kernel reads operands through its tensor maps)
+  const float* A;
+  const float* W;
+  int kpad;
+};
+
+constexpr int kFcBlockM = 128;
+constexpr int kFcThreads = 192;          // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+constexpr int kFcSmemBytes = 227 * 1024;
+
+template <int S, int BN>
+struct FcTcCfg {
+  using Sch = Scheme<S>;
+  static constexpr int kABytes = kFcBlockM * 128;            // one A plane tile: 128 rows x 128 B
+  static constexpr int kBBytes = BN * 128;                   // one W plane tile
+  static constexpr int kStageBytes = Sch::kPlanes * (kABytes + kBBytes);
+  static constexpr int kAuxBytes = 2048 + 2 * BN * 4;        // barriers + bias tiles
+  static constexpr int kStagesRaw = (kFcSmemBytes - 1024 - kAuxBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
+  static_assert(kStages >= 2, "need at least a double-buffered operand ring");
+  static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "power-of-two TMEM allocation");
+};
+
+// One 32-column chunk of one row: bias, activation, then either split planes or float32.
+template <int S>
+__device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const uint32_t (&r)[32], const float* sbias,
+                                                  int row, int n0, bool& ovf) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = fmaf(__uint_as_float(r[j]), a.alpha, sbias[j]);
+    if (a.relu) x = fmaxf(x, 0.0f);
+    v[j] = x;
+  }
+  if (a.out_planes) {
+    if (n0 >= a.out_kpad) return;
+    constexpr int kWords = 32 * sizeof(E) / 4;            // 32-bit words per plane per chunk
+    uint32_t pk[Sch::kPlanes][kWords];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      E p0[Sch::kPlanes], p1[Sch::kPlanes];
+      Sch::split(v[j], a.out_scale, p0, &ovf);
+      Sch::split(v[j + 1], a.out_scale, p1, &ovf);
+#pragma unroll
+      for (int q = 0; q < Sch::kPlanes; ++q) {
+        if constexpr (sizeof(E) == 4) {
+          pk[q][j] = __float_as_uint(*reinterpret_cast<const float*>(&p0[q]));
+          pk[q][j + 1] = __float_as_uint(*reinterpret_cast<const float*>(&p1[q]));
+        } else {
+          const uint32_t lo = *reinterpret_cast<const uint16_t*>(&p0[q]);
+          const uint32_t hi = *reinterpret_cast<const uint16_t*>(&p1[q]);
+          pk[q][j >> 1] = lo | (hi << 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Sch::kPlanes; ++q) {
+      E* dst = reinterpret_cast<E*>(a.out_planes) +
+               (static_cast<size_t>(q) * a.out_plane_rows + row) * a.out_kpad + n0;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < kWords / 4; ++i)
+        d4[i] = make_uint4(pk[q][4 * i], pk[q][4 * i + 1], pk[q][4 * i + 2], pk[q][4 * i + 3]);
+    }
+  } else {
+    float* dst = a.out_f32 + static_cast<size_t>(row) * a.out_ld + n0;
+    if (n0 + 32 <= a.N && (a.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < a.N) dst[j] = v[j];
+    }
+  }
+}
+
+template <int S, int BN>
+__global__ void __launch_bounds__(kFcThreads, 1)
+fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const FcArgs a) {
+  using Cfg = FcTcCfg<S, BN>;
+  using Sch = Scheme<S>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kPlanes = Sch::kPlanes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aux = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [kStages]
+  uint64_t* empty_bar = full_bar + kStages;                         // [kStages]
+  uint64_t* tfull_bar = empty_bar + kStages;                        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* cta_abort = tmem_slot + 1;
+  float* sbias = reinterpret_cast<float*>(aux + 2048);              // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (a.M + kFcBlockM - 1) / kFcBlockM;
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 4);       // one arrive per epilogue warp
+    }
+    *cta_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+          if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+#pragma unroll
+          for (int p = 0; p < kPlanes; ++p)
+            tma_load_2d(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
+                        p * a.a_plane_rows + m_blk * kFcBlockM);
+#pragma unroll
+          for (int p = 0; p < kPlanes; ++p)
+            tma_load_2d(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,
+                        kb * Sch::kBlockK, p * a.b_plane_rows + n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(Sch::kFmt, kFcBlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) break;
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+          if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kPlanes * Cfg::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {          // 4 k-steps of 32 bytes inside the 128-byte swizzle row
+#pragma unroll
+            for (int ps = 0; ps < Sch::kPasses; ++ps) {
+              const uint64_t da = umma_desc_sw128(sa + pass_a(ps) * Cfg::kABytes + ks * 32);
+              const uint64_t db = umma_desc_sw128(sb + pass_b(ps) * Cfg::kBBytes + ks * 32);
+              umma_ss<Sch::kTf32>(tmem_d, da, db, idesc, (kb | ks | ps) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + stage);           // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(tfull_bar + acc);       // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM -> regs -> global) =================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int et = (warp - 2) * 32 + lane;          // 0..127 among epilogue threads
+    bool ovf = false;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      float* sb = sbias + acc * BN;
+      for (int i = et; i < BN; i += 128) {
+        const int n = n_blk * BN + i;
+        sb[i] = (n < a.N) ? __ldg(a.bias + n) : 0.0f;
+      }
+      named_bar_sync(1, 128);
+      if (!mbar_wait(tfull_bar + acc, acc_phase, cta_abort, a.flags)) break;
+      tc_fence_after_sync();
+      const int row = m_blk * kFcBlockM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (row < a.M) fc_epilogue_chunk<S>(a, r, sb + c * 32, row, n_blk * BN + c * 32, ovf);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+    }
+    if (ovf) atomicOr(a.flags, kFlagRange);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact FP32 CUDA-core GEMM: 128x128 tile, 256 threads, 8x8 micro-tile, BK = 16.
+// A [rows_alloc][kpad] and W [Npad][kpad] are both K-major and zero padded, so no K masking.
+template <int S>
+__global__ void __launch_bounds__(256) fc_simt_kernel(const FcArgs a) {
+  static_assert(S == kFp32Simt, "SIMT path stores single-plane fp32 operands");
+  constexpr int BM = 128, BNs = 128, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BNs + 4];
+  const int n_tiles = (a.N + BNs - 1) / BNs;
+  const int m_blk = blockIdx.x / n_tiles, n_blk = blockIdx.x % n_tiles;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const float* Ab = a.A + static_cast<size_t>(m_blk) * BM * a.kpad;
+  const float* Wb = a.W + static_cast<size_t>(n_blk) * BNs * a.kpad;
+  for (int k0 = 0; k0 < a.kpad; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + i * 256;        // 512 float4 per operand tile
+      const int r = idx >> 2, kq = (idx & 3) * 4;
+      const float4 va = *reinterpret_cast<const float4*>(Ab + static_cast<size_t>(r) * a.kpad + k0 + kq);
+      As[kq + 0][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
+      const float4 vw = *reinterpret_cast<const float4*>(Wb + static_cast<size_t>(r) * a.kpad + k0 + kq);
+      Ws[kq + 0][r] = vw.x; Ws[kq + 1][r] = vw.y; Ws[kq + 2][r] = vw.z; Ws[kq + 3][r] = vw.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float ar[8], wr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ar[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wr[j] = Ws[kk][tx * 8 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_blk * BM + ty * 8 + i;
+    if (row >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n_blk * BNs + tx * 8 + j;
+      float x = 0.f;
+      if (n < a.N) {
+        x = fmaf(acc[i][j], a.alpha, __ldg(a.bias + n));
+        if (a.relu) x = fmaxf(x, 0.f);
+      }
+      if (a.out_planes) {
+        if (n < a.out_kpad)
+          reinterpret_cast<float*>(a.out_planes)[static_cast<size_t>(row) * a.out_kpad + n] = x * a.out_scale;
+      } else if (n < a.N) {
+        a.out_f32[static_cast<size_t>(row) * a.out_ld + n] = x;
+      }
+    }
+  }
+}
+
+}  // namespace mm

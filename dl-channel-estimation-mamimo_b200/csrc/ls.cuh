@@ -1,0 +1,222 @@
+// LS channel estimate + comb-pilot interpolation + operand staging (HBM-bound stage).
+//
+// Replaces the Nr x Nt interpreted loop of
+//   packet_generation/phased_arr/helperMIMOChannelEstimate.m:33-36
+//     hD(:,j,i) = rxsym*Puse(:,j)./denom ,  Puse = P', denom = nltf.*ltf(ind)
+// for a whole batch of packets in one launch:
+//   H[p,i,j,k] = ( sum_n Y[p,i,n,k] * conj(P[j,n]) ) * inv_denom[k],  inv_denom = 1/(nltf * X_pilot)
+//
+// One CTA owns (packet, rx antenna, tile of pilots).  Phase 1: each thread owns one pilot
+// tone, pulls its n_ltf received symbols with coalesced float2/double2 loads (k is the
+// contiguous axis of Y), despreads them in registers -- a fast Walsh-Hadamard transform when
+// P is Sylvester-Hadamard, a dense complex matvec against P in shared memory otherwise --
+// and parks the Nt results in shared memory.  Phase 2: the CTA sweeps (tx, k) with k fastest,
+// interpolates between pilots when n_ps > 1 (n_ps == 1 is a pure copy: bit-exact identity),
+// and writes (a) the user-visible H_ls and (b) the first FC layer's split operand planes for
+// the real and the imaginary net, all with coalesced stores.
+#pragma once
+#include "ptx.cuh"
+#include "schemes.cuh"
+
+namespace mm {
+
+struct LsArgs {
+  const void* Y;          // complex [n_pkt][n_rx][n_ltf][n_sc_in]  (float2 or double2)
+  const float2* P;        // [n_tx][n_ltf] (dense path only)
+  const float2* inv_den;  // [n_pil]  1 / (n_ltf * X_pilot)
+  void* H_ls;             // optional complex [n_pkt][n_rx][n_tx][n_sc] (float2 or double2)
+  void* planes[2];        // optional: layer-1 operand of net 0 (real part) / net 1 (imag part)
+  int plane_rows;         // rows_alloc of those operands
+  int kpad;               // row pitch (elements)
+  float scale;            // operand scale (power of two)
+  int n_pkt, n_rx, n_tx, n_ltf, n_sc, n_ps, n_pil;
+  int pil_per_tile;       // pilots per CTA
+  int y_double, h_double;
+  uint32_t* flags;
+};
+
+template <int NLTF>
+__device__ __forceinline__ void fwht(float2 (&v)[NLTF]) {
+#pragma unroll
+  for (int h = 1; h < NLTF; h <<= 1) {
+#pragma unroll
+    for (int i = 0; i < NLTF; ++i) {
+      if ((i & h) == 0) {
+        const float2 a = v[i], b = v[i + h];
+        v[i] = make_float2(a.x + b.x, a.y + b.y);
+        v[i + h] = make_float2(a.x - b.x, a.y - b.y);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float2 ld_y(const void* Y, size_t idx, int is_double) {
+  if (is_double) {
+    const double2 d = __ldg(reinterpret_cast<const double2*>(Y) + idx);
+    return make_float2(static_cast<float>(d.x), static_cast<float>(d.y));
+  }
+  return __ldg(reinterpret_cast<const float2*>(Y) + idx);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// HAD: P is Sylvester-Hadamard and n_tx == n_ltf == NLTF -> FWHT despread.  Otherwise a dense complex
+// matvec against P (shared memory); NLTF > 0 unrolls it over registers, NLTF == 0 is the any-size
+// (n_ltf <= 64) fallback.
+template <int S, int NLTF, bool HAD>
+__global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  extern __shared__ float2 sm_ls[];
+  const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
+  const int tile = blockIdx.x % n_tiles;
+  const int prx = blockIdx.x / n_tiles;                 // pkt * n_rx + rx
+  const int pil0 = tile * a.pil_per_tile;
+  // pilots held by this CTA: [lo, hi) = tile pilots plus one halo pilot on each side (interp only)
+  const int lo = (a.n_ps > 1 && pil0 > 0) ? pil0 - 1 : pil0;
+  int hi = min(pil0 + a.pil_per_tile, a.n_pil);
+  if (a.n_ps > 1 && hi < a.n_pil) hi += 1;
+  const int n_hold = hi - lo;
+  const int pitch = a.pil_per_tile + 3;                 // odd pitch: conflict-free column sweeps
+  float2* sh = sm_ls;                                   // [n_tx][pitch]
+  float2* sP = sm_ls + static_cast<size_t>(a.n_tx) * pitch;   // dense path: [n_tx][n_ltf]
+
+  if constexpr (!HAD) {
+    for (int i = threadIdx.x; i < a.n_tx * a.n_ltf; i += blockDim.x) sP[i] = a.P[i];
+    __syncthreads();
+  }
+
+  // ---- phase 1: despread at pilot tones -------------------------------------------------
+  const size_t y_base = static_cast<size_t>(prx) * a.n_ltf * a.n_sc;
+  for (int t = threadIdx.x; t < n_hold; t += blockDim.x) {
+    const int pil = lo + t;
+    const int k = pil * a.n_ps;
+    const float2 inv = __ldg(a.inv_den + pil);
+    if constexpr (HAD) {
+      float2 v[NLTF];
+#pragma unroll
+      for (int n = 0; n < NLTF; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
+      fwht<NLTF>(v);
+#pragma unroll
+      for (int j = 0; j < NLTF; ++j) sh[j * pitch + t] = cmul(v[j], inv);
+    } else if constexpr (NLTF > 0) {
+      float2 v[NLTF];
+#pragma unroll
+      for (int n = 0; n < NLTF; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
+      for (int j = 0; j < a.n_tx; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NLTF; ++n) {
+          const float2 p = sP[j * NLTF + n];              // y * conj(p)
+          acc.x += v[n].x * p.x + v[n].y * p.y;
+          acc.y += v[n].y * p.x - v[n].x * p.y;
+        }
+        sh[j * pitch + t] = cmul(acc, inv);
+      }
+    } else {
+      for (int j = 0; j < a.n_tx; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int n = 0; n < a.n_ltf; ++n) {
+          const float2 y = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
+          const float2 p = sP[j * a.n_ltf + n];
+          acc.x += y.x * p.x + y.y * p.y;
+          acc.y += y.y * p.x - y.x * p.y;
+        }
+        sh[j * pitch + t] = cmul(acc, inv);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: interpolate + emit ------------------------------------------------------
+  const int k0 = pil0 * a.n_ps;
+  const int k1 = (pil0 + a.pil_per_tile >= a.n_pil) ? a.n_sc : min(a.n_sc, (pil0 + a.pil_per_tile) * a.n_ps);
+  const int nk = k1 - k0;
+  bool ovf = false;
+  const float inv_nps = 1.0f / static_cast<float>(a.n_ps);
+  for (int idx = threadIdx.x; idx < a.n_tx * nk; idx += blockDim.x) {
+    const int j = idx / nk;
+    const int k = k0 + (idx - j * nk);
+    float2 h;
+    if (a.n_ps == 1) {
+      h = sh[j * pitch + (k - k0)];
+    } else if (a.n_pil == 1) {
+      h = sh[j * pitch];
+    } else {
+      const int seg = min(k / a.n_ps, a.n_pil - 2);
+      const float w = static_cast<float>(k - seg * a.n_ps) * inv_nps;
+      const float2 h0 = sh[j * pitch + (seg - lo)];
+      const float2 h1 = sh[j * pitch + (seg + 1 - lo)];
+      h = make_float2(h0.x + w * (h1.x - h0.x), h0.y + w * (h1.y - h0.y));
+    }
+    const size_t row = static_cast<size_t>(prx) * a.n_tx + j;
+    if (a.H_ls) {
+      if (a.h_double) reinterpret_cast<double2*>(a.H_ls)[row * a.n_sc + k] = make_double2(h.x, h.y);
+      else reinterpret_cast<float2*>(a.H_ls)[row * a.n_sc + k] = h;
+    }
+    if (a.planes[0]) {
+      E pr[Sch::kPlanes], pi[Sch::kPlanes];
+      Sch::split(h.x, a.scale, pr, &ovf);
+      Sch::split(h.y, a.scale, pi, &ovf);
+#pragma unroll
+      for (int pl = 0; pl < Sch::kPlanes; ++pl) {
+        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+        reinterpret_cast<E*>(a.planes[0])[off] = pr[pl];
+        reinterpret_cast<E*>(a.planes[1])[off] = pi[pl];
+      }
+    }
+  }
+  if (ovf) atomicOr(a.flags, kFlagRange);
+}
+
+// ---- mode B: caller planes float32 [rows][d_in] -> operand planes (inference.py:29-30) ----
+template <int S>
+__global__ void stage_planes_kernel(const float* __restrict__ X, void* planes, int64_t rows, int d_in,
+                                    int plane_rows, int kpad, float scale, uint32_t* flags) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  bool ovf = false;
+  const int64_t total = rows * d_in;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d_in;
+    const int c = static_cast<int>(i - r * d_in);
+    E p[Sch::kPlanes];
+    Sch::split(__ldg(X + i), scale, p, &ovf);
+#pragma unroll
+    for (int pl = 0; pl < Sch::kPlanes; ++pl)
+      reinterpret_cast<E*>(planes)[(static_cast<size_t>(pl) * plane_rows + r) * kpad + c] = p[pl];
+  }
+  if (ovf) atomicOr(flags, kFlagRange);
+}
+
+// ---- mode A: [time-domain LTF || P(:,iTx)] per pair (massiveMIMO_dataGenerator.py:303-316) ----
+// sig float32 [n_pkt][n_rx][len_ltf]; row = (pkt*n_rx + rx)*n_tx + j gets sig[pkt][rx][:] then Re P[j][0..n_tx)
+template <int S>
+__global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2* __restrict__ P, void* planes,
+                                    int64_t n_prx, int n_tx, int n_ltf, int len_ltf, int plane_rows, int kpad,
+                                    float scale, uint32_t* flags) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  bool ovf = false;
+  const int d_in = len_ltf + n_tx;
+  const int64_t total = n_prx * n_tx * d_in;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d_in;
+    const int c = static_cast<int>(i - r * d_in);
+    const int64_t prx = r / n_tx;
+    const int j = static_cast<int>(r - prx * n_tx);
+    const float x = (c < len_ltf) ? __ldg(sig + prx * len_ltf + c) : P[j * n_ltf + (c - len_ltf)].x;
+    E p[Sch::kPlanes];
+    Sch::split(x, scale, p, &ovf);
+#pragma unroll
+    for (int pl = 0; pl < Sch::kPlanes; ++pl)
+      reinterpret_cast<E*>(planes)[(static_cast<size_t>(pl) * plane_rows + r) * kpad + c] = p[pl];
+  }
+  if (ovf) atomicOr(flags, kFlagRange);
+}
+
+}  // namespace mm

@@ -1,0 +1,123 @@
+// Operand storage schemes of the FC layers.
+//
+// The FC layers must agree with an FP32 TensorFlow reference to <= 1e-5 relative L2
+// (BASELINE.json north_star), but tcgen05 has no FP32 input kind.  Every FP32 operand
+// x is therefore stored as a small sum of low-precision "planes" x ~= p0 + p1 and the
+// product A.B is accumulated (FP32, in TMEM) as p0.q0 + p0.q1 + p1.q0 -- the dropped
+// p1.q1 term is ~2^-22 relative.  A plane is a K-major [rows][Kpad] matrix; planes of one
+// operand are stacked along the row axis so a single 2-D TMA map addresses all of them.
+//
+//   scheme     elem  planes  MMA kind    passes  operand error      range
+//   FP32_SIMT  f32   1       (FFMA)      -       exact fp32         fp32
+//   TF32X3     f32   2       kind::tf32  3       ~2^-21             fp32 (robust)
+//   FP16X3     f16   2       kind::f16   3       ~2^-22 (scaled)    |x|*2^s < 65504, checked
+//   BF16X1     bf16  1       kind::f16   1       2^-9  (diagnostic) fp32
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mm {
+
+enum : int { kFp32Simt = 0, kTf32x3 = 1, kFp16x3 = 2, kBf16x1 = 3 };
+
+template <int S>
+struct Scheme;
+
+template <>
+struct Scheme<kFp32Simt> {
+  using elem = float;
+  static constexpr int kPlanes = 1;
+  static constexpr int kBlockK = 32;        // K padding granule (elements)
+  __host__ __device__ static void split(float x, float scale, elem* p, bool* overflow) {
+    (void)overflow;
+    p[0] = x * scale;
+  }
+};
+
+template <>
+struct Scheme<kTf32x3> {
+  using elem = float;                       // tf32 operands live in 32-bit containers
+  static constexpr int kPlanes = 2;
+  static constexpr int kBlockK = 32;        // 128-byte swizzle row
+  static constexpr int kUmmaK = 8;
+  static constexpr uint32_t kFmt = 2;       // F16F32Format::TF32
+  static constexpr bool kTf32 = true;
+  static constexpr int kPasses = 3;
+  __host__ __device__ static float round_tf32(float x) {
+    // round-to-nearest (ties away) to 10 explicit mantissa bits, done on the bit pattern so
+    // host (weight split) and device (activation split) agree exactly
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(x);
+#else
+    memcpy(&u, &x, 4);
+#endif
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;    // inf / nan untouched
+    u += 0x1000u;
+    u &= 0xffffe000u;
+    float r;
+#ifdef __CUDA_ARCH__
+    r = __uint_as_float(u);
+#else
+    memcpy(&r, &u, 4);
+#endif
+    return r;
+  }
+  __host__ __device__ static void split(float x, float scale, elem* p, bool* overflow) {
+    (void)overflow;
+    const float v = x * scale;
+    const float hi = round_tf32(v);
+    p[0] = hi;
+    p[1] = v - hi;          // exact in fp32; the MMA truncates it to tf32 (error ~2^-23 |v|)
+  }
+};
+
+template <>
+struct Scheme<kFp16x3> {
+  using elem = __half;
+  static constexpr int kPlanes = 2;
+  static constexpr int kBlockK = 64;
+  static constexpr int kUmmaK = 16;
+  static constexpr uint32_t kFmt = 0;       // F16
+  static constexpr bool kTf32 = false;
+  static constexpr int kPasses = 3;
+  __host__ __device__ static void split(float x, float scale, elem* p, bool* overflow) {
+    const float v = x * scale;              // scale is a power of two: exact
+    if (!(fabsf(v) <= 65504.0f)) *overflow = true;
+    const __half hi = __float2half_rn(v);
+    p[0] = hi;
+    p[1] = __float2half_rn(v - __half2float(hi));
+  }
+};
+
+template <>
+struct Scheme<kBf16x1> {
+  using elem = __nv_bfloat16;
+  static constexpr int kPlanes = 1;
+  static constexpr int kBlockK = 64;
+  static constexpr int kUmmaK = 16;
+  static constexpr uint32_t kFmt = 1;       // BF16
+  static constexpr bool kTf32 = false;
+  static constexpr int kPasses = 1;
+  __host__ __device__ static void split(float x, float scale, elem* p, bool* overflow) {
+    (void)overflow;
+    p[0] = __float2bfloat16_rn(x * scale);
+  }
+};
+
+// (A plane, B plane) of pass i -- smallest terms last so the dominant product opens the accumulator
+__host__ __device__ constexpr int pass_a(int i) { return i == 2 ? 1 : 0; }
+__host__ __device__ constexpr int pass_b(int i) { return i == 1 ? 1 : 0; }
+
+// A K-major operand: `planes` stacked [plane][rows_alloc][kpad] matrices of elem
+struct Operand {
+  void* ptr = nullptr;
+  int planes = 0;
+  int rows_alloc = 0;      // plane stride in rows (multiple of the row tile)
+  int kpad = 0;            // row pitch in elements (multiple of kBlockK)
+  int elem_bytes = 0;
+  size_t bytes() const { return static_cast<size_t>(planes) * rows_alloc * kpad * elem_bytes; }
+};
+
+}  // namespace mm

@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference's call surfaces over the C ABI (include/mamimo.h).
+
+  Engine                      -- thin object wrapper of mamimo_engine (all math is in the CUDA library)
+  helperMIMOChannelEstimate   -- MATLAB-shaped drop-in for pg/helperMIMOChannelEstimate.m:1 (LS part)
+  CSIPredictor                -- drop-in for inference.py:6-68
+
+numpy arrays are treated as HOST buffers (the library streams them through the GPU);
+torch CUDA tensors are treated as DEVICE buffers (no copies, launched on torch's current stream).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from . import _capi
+from ._capi import lib, check
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory from mamimo_host_alloc (freed with the array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib.mamimo_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError("mamimo_host_alloc(%d) failed" % n)
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            lib.mamimo_host_free(self.ptr)
+
+    # keep the allocation alive as long as any view of arr lives
+    holder = _Owner(p)
+    arr = arr.view(_PinnedArray)
+    arr._holder = holder
+    return arr
+
+
+class _PinnedArray(np.ndarray):
+    def __array_finalize__(self, obj):
+        self._holder = getattr(obj, "_holder", None)
+
+
+class Engine:
+    """One engine per device.  See include/mamimo.h for the contract of every call."""
+
+    def __init__(self, n_tx, n_rx, n_sc, n_ltf=None, n_ps=1, hidden=(1024, 1024), d_in=None, d_out=None,
+                 input_mode="ls", precision="tf32x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=6,
+                 mlp=True):
+        cfg = _capi.Config()
+        lib.mamimo_config_init(C.byref(cfg))
+        cfg.device = device
+        cfg.n_tx, cfg.n_rx, cfg.n_sc = n_tx, n_rx, n_sc
+        cfg.n_ltf = n_tx if n_ltf is None else n_ltf
+        cfg.n_ps = n_ps
+        cfg.input_mode = _capi.INPUT_MODES[input_mode]
+        cfg.precision = _capi.PRECISIONS[precision]
+        hidden = tuple(hidden) if mlp else ()
+        if len(hidden) > _capi.MAX_HIDDEN:
+            raise ValueError("at most %d hidden layers" % _capi.MAX_HIDDEN)
+        cfg.n_hidden = len(hidden)
+        for i, h in enumerate(hidden):
+            cfg.hidden[i] = int(h)
+        if mlp:
+            cfg.d_in = int(d_in if d_in is not None else (n_sc if input_mode == "ls" else len_ltf + n_tx))
+            cfg.d_out = int(d_out if d_out is not None else n_sc)
+        cfg.len_ltf = len_ltf
+        cfg.max_pkts = max_pkts
+        cfg.act_scale_log2 = act_scale_log2
+        self.cfg = cfg
+        self.precision = precision
+        self.input_mode = input_mode
+        self._h = C.c_void_p()
+        check(lib.mamimo_create(C.byref(cfg), C.byref(self._h)))
+        self.rows_per_pkt = n_tx * n_rx
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.mamimo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ tables / weights
+    def set_pilots(self, x_pilot=None, P=None):
+        """x_pilot [n_pilots] (ltf(ind), helperMIMOChannelEstimate.m:27) and P [n_tx, n_ltf] (helperGetP, :13)."""
+        xp = None if x_pilot is None else np.ascontiguousarray(np.asarray(x_pilot, dtype=np.complex64))
+        Pm = None if P is None else np.ascontiguousarray(np.asarray(P, dtype=np.complex64))
+        if Pm is not None and Pm.shape != (self.cfg.n_tx, self.cfg.n_ltf):
+            raise ValueError("P must be [n_tx, n_ltf]")
+        n_pil = (self.cfg.n_sc + self.cfg.n_ps - 1) // self.cfg.n_ps
+        if xp is not None and xp.shape != (n_pil,):
+            raise ValueError("x_pilot must have %d entries" % n_pil)
+        check(lib.mamimo_set_pilots(self._h, None if xp is None else _np_ptr(xp), None if Pm is None else _np_ptr(Pm)),
+              self._h)
+
+    def load_weights(self, nets):
+        """nets = {'real': layers, 'imag': layers}; layer = dict(W [in,out] (Keras kernel), b [out],
+        bn = None | (gamma, beta, moving_mean, moving_var)).  Mirrors Model.load_weights (..._DNN.py:334)."""
+        f32 = lambda t: np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+        for net, name in enumerate(("real", "imag")):
+            for li, L in enumerate(nets[name]):
+                W, b = f32(L["W"]), f32(L["b"])
+                bn = L.get("bn")
+                bnp = [f32(t) for t in bn] if bn is not None else [None] * 4
+                args = [_np_ptr(W), _np_ptr(b)] + [None if t is None else _np_ptr(t) for t in bnp]
+                check(lib.mamimo_load_layer(self._h, net, li, *args), self._h)
+        check(lib.mamimo_finalize_weights(self._h), self._h)
+
+    # ------------------------------------------------------------------ raw pointer calls (bench / C-ABI parity tests)
+    def estimate_raw(self, y_ptr, y_type, n_pkt, hls_ptr, hr_ptr, hi_ptr, mem, stream=0):
+        check(lib.mamimo_estimate(self._h, C.c_void_p(y_ptr), y_type, n_pkt, C.c_void_p(hls_ptr) if hls_ptr else None,
+                                  C.c_void_p(hr_ptr), C.c_void_p(hi_ptr), mem, C.c_void_p(stream) if stream else None),
+              self._h)
+
+    def ls_estimate_raw(self, y_ptr, y_type, n_pkt, h_ptr, h_type, mem, stream=0):
+        check(lib.mamimo_ls_estimate(self._h, C.c_void_p(y_ptr), y_type, mem, n_pkt, C.c_void_p(h_ptr), h_type, mem,
+                                     C.c_void_p(stream) if stream else None), self._h)
+
+    # ------------------------------------------------------------------ array-level calls
+    def _y_info(self, Y):
+        c = self.cfg
+        if tuple(Y.shape[1:]) != (c.n_rx, c.n_ltf, c.n_sc):
+            raise ValueError("Y must be [n_pkt, n_rx=%d, n_ltf=%d, n_sc=%d], got %s"
+                             % (c.n_rx, c.n_ltf, c.n_sc, tuple(Y.shape)))
+        return int(Y.shape[0])
+
+    def ls_estimate(self, Y):
+        """Y [n_pkt, n_rx, n_ltf, n_sc] complex64/complex128 -> H_ls [n_pkt, n_rx, n_tx, n_sc] (same dtype)."""
+        n_pkt = self._y_info(Y)
+        c = self.cfg
+        if _is_torch_cuda(Y):
+            import torch
+            if Y.dtype not in (torch.complex64, torch.complex128):
+                raise TypeError("Y must be complex64 or complex128")
+            Y = Y.contiguous()
+            H = torch.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=Y.dtype, device=Y.device)
+            t = _capi.C128 if Y.dtype == torch.complex128 else _capi.C64
+            self.ls_estimate_raw(Y.data_ptr(), t, n_pkt, H.data_ptr(), t, _capi.MEM_DEVICE,
+                                 torch.cuda.current_stream(Y.device).cuda_stream)
+            return H
+        Y = np.ascontiguousarray(Y)
+        if Y.dtype not in (np.complex64, np.complex128):
+            raise TypeError("Y must be complex64 or complex128")
+        t = _capi.C128 if Y.dtype == np.complex128 else _capi.C64
+        H = np.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=Y.dtype)
+        self.ls_estimate_raw(Y.ctypes.data, t, n_pkt, H.ctypes.data, t, _capi.MEM_HOST)
+        return H
+
+    def estimate(self, Y, want_ls=False):
+        """Full path (mode C).  Returns (H_real, H_imag[, H_ls]); H_* float32 [n_pkt*n_rx*n_tx, d_out]."""
+        n_pkt = self._y_info(Y)
+        c = self.cfg
+        rows = n_pkt * self.rows_per_pkt
+        if _is_torch_cuda(Y):
+            import torch
+            Y = Y.contiguous()
+            t = _capi.C128 if Y.dtype == torch.complex128 else _capi.C64
+            Hr = torch.empty((rows, c.d_out), dtype=torch.float32, device=Y.device)
+            Hi = torch.empty_like(Hr)
+            Hls = torch.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=torch.complex64, device=Y.device) if want_ls else None
+            self.estimate_raw(Y.data_ptr(), t, n_pkt, Hls.data_ptr() if want_ls else 0, Hr.data_ptr(), Hi.data_ptr(),
+                              _capi.MEM_DEVICE, torch.cuda.current_stream(Y.device).cuda_stream)
+        else:
+            Y = np.ascontiguousarray(Y)
+            if Y.dtype not in (np.complex64, np.complex128):
+                raise TypeError("Y must be complex64 or complex128")
+            t = _capi.C128 if Y.dtype == np.complex128 else _capi.C64
+            Hr = np.empty((rows, c.d_out), dtype=np.float32)
+            Hi = np.empty_like(Hr)
+            Hls = np.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=np.complex64) if want_ls else None
+            self.estimate_raw(Y.ctypes.data, t, n_pkt, Hls.ctypes.data if want_ls else 0, Hr.ctypes.data,
+                              Hi.ctypes.data, _capi.MEM_HOST)
+        return (Hr, Hi, Hls) if want_ls else (Hr, Hi)
+
+    def predict_planes(self, X_real, X_imag):
+        """Mode B: float32 [rows, d_in] x2 -> float32 [rows, d_out] x2 (inference.py:29-30)."""
+        c = self.cfg
+        if _is_torch_cuda(X_real):
+            import torch
+            Xr, Xi = X_real.contiguous().float(), X_imag.contiguous().float()
+            rows = int(Xr.shape[0])
+            Yr = torch.empty((rows, c.d_out), dtype=torch.float32, device=Xr.device)
+            Yi = torch.empty_like(Yr)
+            check(lib.mamimo_predict_planes(self._h, C.c_void_p(Xr.data_ptr()), C.c_void_p(Xi.data_ptr()), rows,
+                                            C.c_void_p(Yr.data_ptr()), C.c_void_p(Yi.data_ptr()), _capi.MEM_DEVICE,
+                                            C.c_void_p(torch.cuda.current_stream(Xr.device).cuda_stream)), self._h)
+            return Yr, Yi
+        Xr = np.ascontiguousarray(X_real, dtype=np.float32)
+        Xi = np.ascontiguousarray(X_imag, dtype=np.float32)
+        if Xr.ndim != 2 or Xr.shape[1] != c.d_in or Xi.shape != Xr.shape:
+            raise ValueError("planes must be [rows, d_in=%d]" % c.d_in)
+        rows = Xr.shape[0]
+        Yr = np.empty((rows, c.d_out), dtype=np.float32)
+        Yi = np.empty_like(Yr)
+        check(lib.mamimo_predict_planes(self._h, _np_ptr(Xr), _np_ptr(Xi), rows, _np_ptr(Yr), _np_ptr(Yi),
+                                        _capi.MEM_HOST, None), self._h)
+        return Yr, Yi
+
+    def predict_time(self, sig_real, sig_imag):
+        """Mode A: float32 [n_pkt, n_rx, len_ltf] x2 -> float32 [n_pkt*n_rx*n_tx, d_out] x2."""
+        c = self.cfg
+        Sr = np.ascontiguousarray(sig_real, dtype=np.float32)
+        Si = np.ascontiguousarray(sig_imag, dtype=np.float32)
+        if Sr.ndim != 3 or tuple(Sr.shape[1:]) != (c.n_rx, c.len_ltf) or Si.shape != Sr.shape:
+            raise ValueError("signals must be [n_pkt, n_rx=%d, len_ltf=%d]" % (c.n_rx, c.len_ltf))
+        n_pkt = Sr.shape[0]
+        Yr = np.empty((n_pkt * self.rows_per_pkt, c.d_out), dtype=np.float32)
+        Yi = np.empty_like(Yr)
+        check(lib.mamimo_predict_time(self._h, _np_ptr(Sr), _np_ptr(Si), n_pkt, _np_ptr(Yr), _np_ptr(Yi),
+                                      _capi.MEM_HOST, None), self._h)
+        return Yr, Yi
+
+    def synchronize(self):
+        check(lib.mamimo_synchronize(self._h), self._h)
+
+    def profile_begin(self):
+        check(lib.mamimo_profile_begin(self._h), self._h)
+
+    def profile_end(self):
+        p = _capi.Profile()
+        check(lib.mamimo_profile_end(self._h, C.byref(p)), self._h)
+        return dict(ls_ms=p.ls_ms, fc_ms=p.fc_ms, stage_ms=p.stage_ms, ls_launches=int(p.ls_launches),
+                    fc_launches=int(p.fc_launches), stage_launches=int(p.stage_launches))
+
+    def stats(self):
+        s = _capi.Stats()
+        check(lib.mamimo_get_stats(self._h, C.byref(s)), self._h)
+        return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes),
+                    last_device_flags=int(s.last_device_flags))
+
+
+# ---------------------------------------------------------------------- integer tables
+def vht_ltf256():
+    out = (C.c_int8 * 256)()
+    lib.mamimo_vht_ltf256(out)
+    return np.frombuffer(out, dtype=np.int8).copy()
+
+
+def carriers_locations():
+    n = lib.mamimo_carriers_locations(None, 0)
+    out = (C.c_int32 * n)()
+    lib.mamimo_carriers_locations(out, n)
+    return np.frombuffer(out, dtype=np.int32).copy()
+
+
+def default_p(n):
+    out = np.empty((n, n), dtype=np.float32)
+    st = lib.mamimo_default_p(n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    if st != _capi.OK:
+        raise ValueError("default P needs a power-of-two size")
+    return out
+
+
+def pair_row(p, i_rx, i_tx, n_rx, n_tx):
+    return int(lib.mamimo_pair_row(p, i_rx, i_tx, n_rx, n_tx))
+
+
+# ---------------------------------------------------------------------- MATLAB-shaped drop-in
+_ENGINE_CACHE = {}
+
+
+def helperMIMOChannelEstimate(rxData, prm, Nps=1, tau=None, SNR=None, isMMSE=False, P=None, ltf=None, device=0):
+    """[hD, P, ltf_o, hDmmse] = helperMIMOChannelEstimate(rxData, prm, Nps, tau, SNR, isMMSE)
+
+    Same argument meaning as pg/helperMIMOChannelEstimate.m:1.  rxData complex [Nsc, nltf, Nr]
+    (MATLAB logical shape) or [Nsc, nltf, Nr, Npkt] for a batch hoisted out of the packet loop;
+    prm needs 'numSTS' and 'CarriersLocations' (1-based, :9,26).  Returns hD [Nsc, numSTS, Nr(, Npkt)]
+    complex128, P, ltf_o = ltf(ind) (:29) and hDmmse = zeros (LMMSE is out of scope: SURVEY 8f-3;
+    isMMSE=True raises NotImplementedError).
+    """
+    if isMMSE:
+        raise NotImplementedError("LMMSE_ce is outside the accelerated hot path (SURVEY.md 8f-3)")
+    get = (lambda k: prm[k]) if isinstance(prm, dict) else (lambda k: getattr(prm, k))
+    num_sts = int(get("numSTS"))
+    ind = np.asarray(get("CarriersLocations"), dtype=np.int64).ravel()
+    rx = np.asarray(rxData)
+    squeeze = rx.ndim == 3
+    if squeeze:
+        rx = rx[..., None]
+    if rx.ndim != 4:
+        raise ValueError("rxData must be [Nsc, nltf, Nr] or [Nsc, nltf, Nr, Npkt]")
+    nsc, nltf, nrx, npkt = rx.shape
+    if nsc != ind.size:
+        raise ValueError("size(rxData,1) must equal numel(prm.CarriersLocations)")
+    if nltf != num_sts:
+        raise ValueError("nltf should be == numSTS (helperMIMOChannelEstimate.m:10)")
+    table = vht_ltf256() if ltf is None else np.asarray(ltf)
+    ltf_o = table[ind - 1].astype(np.float64)
+    Pm = default_p(num_sts).astype(np.float64) if P is None else np.asarray(P)[:num_sts, :num_sts]
+    key = (num_sts, nrx, nsc, device)
+    eng = _ENGINE_CACHE.get(key)
+    if eng is None:
+        eng = _ENGINE_CACHE[key] = Engine(num_sts, nrx, nsc, mlp=False, device=device)
+    eng.set_pilots(ltf_o, Pm)
+    # MATLAB [Nsc, nltf, Nr, Npkt] column-major == C-order [Npkt, Nr, nltf, Nsc]
+    Y = np.ascontiguousarray(np.transpose(rx, (3, 2, 1, 0)).astype(np.complex128, copy=False))
+    H = eng.ls_estimate(Y)                                   # [Npkt, Nr, Nt, Nsc]
+    hD = np.transpose(H, (3, 2, 1, 0))
+    if squeeze:
+        hD = hD[..., 0]
+    return hD, Pm, ltf_o.reshape(-1, 1), np.zeros_like(hD)
+
+
+# ---------------------------------------------------------------------- inference.py drop-in
+class CSIPredictor:
+    """Drop-in for inference.py:6-68 backed by the CUDA engine (mode B).
+
+    model_path holds 'real_weights.npz' / 'imag_weights.npz' (flat exports of the Keras layers:
+    W0,b0[,bn0_gamma,bn0_beta,bn0_mean,bn0_var],W1,...; TensorFlow/h5py are not needed) or is
+    given directly as nets={'real': layers, 'imag': layers}.
+    """
+
+    def __init__(self, model_path=None, experiment="RICE_RENEW", verbose=False, nets=None, precision="tf32x3",
+                 device=0):
+        self.path = model_path
+        self.experiment = experiment
+        self.verbose = verbose
+        self.nets = nets if nets is not None else self.load_model()
+        real = self.nets["real"]
+        d_in = int(np.asarray(real[0]["W"]).shape[0])
+        hidden = [int(np.asarray(L["W"]).shape[1]) for L in real[:-1]]
+        d_out = int(np.asarray(real[-1]["W"]).shape[1])
+        self.engine = Engine(1, 1, 1, n_ltf=1, hidden=hidden, d_in=d_in, d_out=d_out, input_mode="planes",
+                             precision=precision, device=device)
+        self.engine.load_weights(self.nets)
+        if verbose:
+            for name in ("real", "imag"):
+                print("------- %s Model Summary -------" % name.capitalize())
+                for i, L in enumerate(self.nets[name]):
+                    print("  dense%d %s bn=%s" % (i, np.asarray(L["W"]).shape, L.get("bn") is not None))
+
+    def load_model(self):
+        nets = {}
+        for name in ("real", "imag"):
+            z = np.load(os.path.join(self.path, name + "_weights.npz"))
+            layers, i = [], 0
+            while "W%d" % i in z:
+                L = {"W": z["W%d" % i], "b": z["b%d" % i], "bn": None}
+                if "bn%d_gamma" % i in z:
+                    L["bn"] = tuple(z["bn%d_%s" % (i, k)] for k in ("gamma", "beta", "mean", "var"))
+                layers.append(L)
+                i += 1
+            nets[name] = layers
+        return nets
+
+    def inference(self, input_batch):
+        X = self.preprocess_data(input_batch)
+        out_r, out_i = self.engine.predict_planes(X.real, X.imag)        # inference.py:29-30
+        return self.postprocess_data(out_r + 1j * out_i)                  # :31-32
+
+    def preprocess_data(self, input_batch):
+        if self.experiment == "RICE_RENEW":
+            if input_batch.dtype != np.complex128:                        # inference.py:41-43
+                print("[CSIPredictor] ERROR: Input batch must be of type np.complex128")
+                sys.exit(-1)
+        return input_batch
+
+    def postprocess_data(self, output_batch):
+        postp = output_batch
+        if self.experiment == "RICE_RENEW":
+            if output_batch.shape[1] == 52:                               # inference.py:56-63
+                n = output_batch.shape[0]
+                tmp = np.concatenate((np.zeros((n, 6)), output_batch[:, 0:26], np.zeros((n, 1)),
+                                      output_batch[:, 26:], np.zeros((n, 5))), axis=1)
+                postp = np.fft.ifftshift(tmp, axes=1)
+            else:                                                          # :64-66
+                print("[CSIPredictor] ERROR: Output samples must have size 52 (assuming FFTLen = 64).")
+                sys.exit(-1)
+        return postp

@@ -1,0 +1,186 @@
+/*
+ * mamimo.h -- C ABI of the B200-native massive-MIMO OFDM channel-estimation engine.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * mauro-belgiovine/DL-channel-estimation-MaMIMO (citations relative to the
+ * reference root; pg/ = packet_generation/phased_arr/):
+ *
+ *   LS estimate (P-matrix despread + divide by LTF tone)     pg/helperMIMOChannelEstimate.m:24-36
+ *   [optional comb-pilot linear interpolation, north_star]   (no reference counterpart; Nps=1 everywhere)
+ *   real/imag FC denoiser per (tx,rx) pair                   massiveMIMO_CSI_prediction_DNN.py:173-234,330-346
+ *   CSIPredictor.inference planes -> two predicts            inference.py:24-32
+ *
+ * Plain C: opaque handle, integer status codes, raw pointers + sizes, no
+ * exceptions, no torch / CUDA types in any signature (streams travel as void*).
+ * The caller owns every buffer it passes; the engine owns weights, tables and
+ * workspace.  One engine per device; calls on one engine are serialised by the
+ * caller (MATLAB's interpreter thread / the Python GIL do that already).
+ *
+ * Layouts (all C order, last index contiguous):
+ *   Y      complex [n_pkt][n_rx][n_ltf][n_sc]   == MATLAB rxData [Nsc x nltf x Nr] per packet (column-major)
+ *   H_ls   complex [n_pkt][n_rx][n_tx][n_sc]    == MATLAB hD     [Nsc x numSTS x Nr] per packet
+ *   H_real / H_imag  float32 [n_pkt*n_rx*n_tx][d_out], row = p*(n_rx*n_tx) + i_rx*n_tx + i_tx
+ *          (create_massiveMIMO_CSIest_dnn_dataset.py:62; inverse pg/BER_test_maMIMO_LTF.m:213-218)
+ */
+#ifndef MAMIMO_H_
+#define MAMIMO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MAMIMO_API __declspec(dllexport)
+#else
+#define MAMIMO_API __attribute__((visibility("default")))
+#endif
+
+#define MAMIMO_ABI_VERSION 1
+#define MAMIMO_MAX_HIDDEN 8
+
+typedef struct mamimo_engine mamimo_engine;
+
+typedef enum {
+  MAMIMO_OK = 0,
+  MAMIMO_ERR_INVALID = 1,      /* bad argument / shape (reference: validateattributes / error(message(...))) */
+  MAMIMO_ERR_CUDA = 2,         /* CUDA runtime / driver failure; see mamimo_last_error */
+  MAMIMO_ERR_NOMEM = 3,
+  MAMIMO_ERR_STATE = 4,        /* e.g. estimate before weights are finalised */
+  MAMIMO_ERR_UNSUPPORTED = 5,  /* e.g. no sm_100 device present */
+  MAMIMO_ERR_RANGE = 6,        /* split-fp16 operand overflow detected on device */
+  MAMIMO_ERR_TIMEOUT = 7       /* a device-side pipeline wait timed out (kernel aborted itself) */
+} mamimo_status;
+
+/* element types of caller buffers */
+typedef enum { MAMIMO_C64 = 0, MAMIMO_C128 = 1 } mamimo_ctype;   /* interleaved re,im (float / double) */
+typedef enum { MAMIMO_MEM_HOST = 0, MAMIMO_MEM_DEVICE = 1 } mamimo_mem;
+
+/* arithmetic of the FC layers (accumulation is always FP32) */
+typedef enum {
+  MAMIMO_PREC_FP32_SIMT = 0,   /* CUDA-core FFMA, exact FP32: on-device accuracy anchor */
+  MAMIMO_PREC_TF32X3 = 1,      /* tcgen05 kind::tf32, error-compensated hi/lo split, 3 MMA passes */
+  MAMIMO_PREC_FP16X3 = 2,      /* tcgen05 kind::f16 (fp16), scaled hi/lo split, 3 MMA passes */
+  MAMIMO_PREC_BF16X1 = 3       /* tcgen05 kind::f16 (bf16), single pass -- NOT within 1e-5; diagnostics only */
+} mamimo_precision;
+
+/* which stage feeds the first FC layer */
+typedef enum {
+  MAMIMO_INPUT_LS = 0,      /* mode C (north_star): real/imag planes of the in-engine LS(+interp) estimate */
+  MAMIMO_INPUT_PLANES = 1,  /* mode B (inference.py:29-30): caller vector, .real -> real net, .imag -> imag net */
+  MAMIMO_INPUT_TIME_P = 2   /* mode A (massiveMIMO_dataGenerator.py:303-316): [time-domain LTF || P(:,iTx)] */
+} mamimo_input_mode;
+
+typedef struct {
+  int32_t abi_version;      /* MAMIMO_ABI_VERSION */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t n_tx;             /* numSTS (helperMIMOChannelEstimate.m:9) */
+  int32_t n_rx;             /* numRx  (:8) */
+  int32_t n_ltf;            /* nltf   (:8); == n_tx during sounding, 1 in the data phase */
+  int32_t n_sc;             /* estimated tones = numel(prm.CarriersLocations) (:26) */
+  int32_t n_ps;             /* pilot spacing; 1 = every tone is a pilot (all reference call sites) */
+  int32_t input_mode;       /* mamimo_input_mode */
+  int32_t precision;        /* mamimo_precision */
+  int32_t d_in;             /* FC input width: mode C n_sc; mode A len_ltf + n_tx; mode B anything */
+  int32_t d_out;            /* FC output width = simParams['nSubCarr'] (..._DNN.py:227) */
+  int32_t n_hidden;         /* number of Dense(relu) layers (--nn), 0 = LS only */
+  int32_t hidden[MAMIMO_MAX_HIDDEN];
+  int32_t len_ltf;          /* mode A only: time-domain samples per (pkt,rx) fed to the net */
+  int32_t max_pkts;         /* packets per internal chunk (workspace sizing); 0 = default */
+  int32_t act_scale_log2;   /* FP16X3 only: power-of-two operand scale (default 6) */
+  int32_t reserved[7];
+} mamimo_config;
+
+typedef struct {
+  uint64_t kernel_launches;   /* engine kernels launched since create */
+  uint64_t h2d_bytes;         /* bytes copied host->device by the engine */
+  uint64_t d2h_bytes;
+  uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout */
+  uint32_t reserved;
+} mamimo_stats;
+
+/* device time per kernel class, measured with CUDA events recorded on the launching stream */
+typedef struct {
+  double ls_ms, fc_ms, stage_ms;                 /* summed event-to-event durations */
+  uint64_t ls_launches, fc_launches, stage_launches;
+} mamimo_profile;
+
+/* ---- library-level ------------------------------------------------------- */
+MAMIMO_API int32_t mamimo_abi_version(void);
+MAMIMO_API const char* mamimo_status_string(mamimo_status s);
+/* last error text for this engine (or the last create failure when e == NULL) */
+MAMIMO_API const char* mamimo_last_error(const mamimo_engine* e);
+MAMIMO_API void mamimo_config_init(mamimo_config* cfg);   /* zero + defaults */
+
+/* ---- integer tables of the reference (bit-exact parity surface) ----------
+ * replaces the literals in pg/helperMIMOChannelEstimate.m:16-23 and
+ * pg/generate_maMIMO_LTF.m:99-102 */
+MAMIMO_API void mamimo_vht_ltf256(int8_t out[256]);
+MAMIMO_API int32_t mamimo_carriers_locations(int32_t* out, int32_t capacity);  /* 1-based; returns count (234) */
+/* default P = Sylvester-Hadamard(n) stand-in for helperGetP (pg/helperMIMOChannelEstimate.m:13) */
+MAMIMO_API mamimo_status mamimo_default_p(int32_t n, float* out /* [n][n] */);
+/* row of pair (p, i_rx, i_tx): create_massiveMIMO_CSIest_dnn_dataset.py:62 */
+MAMIMO_API int64_t mamimo_pair_row(int64_t p, int32_t i_rx, int32_t i_tx, int32_t n_rx, int32_t n_tx);
+
+/* ---- engine lifetime ----------------------------------------------------- */
+MAMIMO_API mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out);
+MAMIMO_API void mamimo_destroy(mamimo_engine* e);
+
+/* pilot tones X_pilot [n_pilots] (complex64 interleaved, n_pilots = ceil(n_sc/n_ps); NULL = all +1) and
+ * mapping matrix P [n_tx][n_ltf] (complex64 interleaved; NULL = default_p).  Replaces ltf(ind) and
+ * helperGetP in pg/helperMIMOChannelEstimate.m:13,27. */
+MAMIMO_API mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P);
+
+/* One Dense layer of net (0 = 'real', 1 = 'imag'); layer in [0, n_hidden].  W is the Keras kernel
+ * [in][out] row-major, b [out]; BN vectors [out] (all NULL when the layer has no BatchNormalization;
+ * the final linear layer never has one).  Replaces Model.load_weights (..._DNN.py:334). */
+MAMIMO_API mamimo_status mamimo_load_layer(mamimo_engine* e, int32_t net, int32_t layer,
+                                           const float* W, const float* b,
+                                           const float* bn_gamma, const float* bn_beta,
+                                           const float* bn_mean, const float* bn_var);
+/* fold BN into the following Dense, split/convert for the selected precision, upload */
+MAMIMO_API mamimo_status mamimo_finalize_weights(mamimo_engine* e);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* LS (+interp) only: drop-in for pg/helperMIMOChannelEstimate.m:33-36 over a batch of packets. */
+MAMIMO_API mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type,
+                                            mamimo_mem y_mem, int64_t n_pkt,
+                                            void* H_ls, mamimo_ctype h_type, mamimo_mem h_mem,
+                                            void* stream);
+
+/* Full path, mode C: Y -> LS -> interp -> two FC nets.  H_ls may be NULL.  mem applies to Y, H_ls,
+ * H_real, H_imag alike.  Host buffers are streamed through the device in chunks of max_pkts with
+ * copies overlapped with compute.  Synchronous w.r.t. the host when mem == HOST; asynchronous on
+ * `stream` when mem == DEVICE. */
+MAMIMO_API mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type,
+                                         int64_t n_pkt, void* H_ls, float* H_real, float* H_imag,
+                                         mamimo_mem mem, void* stream);
+
+/* Mode B: rows of caller-supplied planes (float32 [n_rows][d_in]) -> (float32 [n_rows][d_out]) x2.
+ * This is what CSIPredictor.inference does with X.real / X.imag (inference.py:29-30). */
+MAMIMO_API mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const float* X_imag,
+                                               int64_t n_rows, float* Y_real, float* Y_imag,
+                                               mamimo_mem mem, void* stream);
+
+/* Mode A: time-domain preamble planes sig_real/sig_imag float32 [n_pkt][n_rx][len_ltf]; the engine
+ * appends P(:,iTx) per pair (massiveMIMO_dataGenerator.py:307-311) and runs both nets. */
+MAMIMO_API mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const float* sig_imag,
+                                             int64_t n_pkt, float* Y_real, float* Y_imag,
+                                             mamimo_mem mem, void* stream);
+
+MAMIMO_API mamimo_status mamimo_synchronize(mamimo_engine* e);
+MAMIMO_API mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out);
+/* begin: bracket every engine kernel with a CUDA event pair on its stream; end: synchronise and sum them */
+MAMIMO_API mamimo_status mamimo_profile_begin(mamimo_engine* e);
+MAMIMO_API mamimo_status mamimo_profile_end(mamimo_engine* e, mamimo_profile* out);
+
+/* pinned host memory helpers for callers that want overlapped copies */
+MAMIMO_API void* mamimo_host_alloc(size_t bytes);
+MAMIMO_API void mamimo_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMIMO_H_ */

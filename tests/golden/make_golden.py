@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running / parsing the REAL reference in the
+build container (where /root/reference exists).  The vectors are committed; the
+GPU box never needs the reference.
+
+What is pinned here:
+  1. ltf256 / carriers: parsed numerically out of the MATLAB source text of
+     helperMIMOChannelEstimate.m:16-23 and generate_maMIMO_LTF.m:99-102.
+  2. inference.py's CSIPredictor.inference() executed unmodified, with a stub
+     ``tensorflow.keras`` whose load_model() returns a deterministic numpy MLP
+     (TensorFlow itself is not installed).  Pins pre/post-processing glue.
+  3. massiveMIMO_dataGenerator.DataGenerator executed unmodified (stub
+     ``tensorflow.keras.utils.Sequence``) on a synthetic pickle-shaped dataset
+     built with create_massiveMIMO_CSIest_dnn_dataset.py:62's row formula.
+     Pins per-pair input assembly and pair ordering.
+
+Usage:  python tests/golden/make_golden.py   (writes next to this file)
+"""
+import os
+import re
+import sys
+import types
+import numpy as np
+
+REF = os.environ.get("MAMIMO_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------- 1. tables
+def _matlab_vec(expr, env):
+    """Evaluate a MATLAB column-vector literal made of numbers, a:b ranges,
+    zeros(n,1) and identifiers in env.  Separators: ';', ',', whitespace."""
+    expr = expr.replace("...", " ")
+    expr = re.sub(r"zeros\((\d+),1\)", lambda m: "Z%s" % m.group(1), expr)
+    out = []
+    for tok in re.split(r"[;,\s]+", expr.strip("[] \n\t'")):
+        if not tok:
+            continue
+        if tok.startswith("Z"):
+            out += [0] * int(tok[1:])
+        elif tok in env:
+            out += list(env[tok])
+        elif ":" in tok:
+            a, b = tok.split(":")
+            out += list(range(int(eval(a)), int(eval(b)) + 1))
+        else:
+            out.append(int(eval(tok)))
+    return out
+
+
+def parse_tables():
+    src = open(os.path.join(REF, "packet_generation/phased_arr/helperMIMOChannelEstimate.m")).read()
+    env = {}
+    for name in ("ltfLeft", "ltfRight", "ltf"):
+        m = re.search(r"^%s\s*=\s*\[(.*?)\];" % name, src, re.S | re.M)
+        env[name] = _matlab_vec(m.group(1), env)
+    gen = open(os.path.join(REF, "packet_generation/phased_arr/generate_maMIMO_LTF.m")).read()
+    nulls = _matlab_vec(re.search(r"prm\.NullCarrierIndices\s*=\s*\[(.*?)\]", gen).group(1), {})
+    pilots = _matlab_vec(re.search(r"prm\.PilotCarrierIndices\s*=\s*\[(.*?)\]", gen).group(1), {})
+    fft_len = int(re.search(r"prm\.FFTLength\s*=\s*(\d+)", gen).group(1))
+    carriers = sorted(set(range(1, fft_len + 1)) - set(nulls) - set(pilots))   # setdiff, :102
+    return dict(ltf256=np.asarray(env["ltf"], np.int8), nulls=np.asarray(nulls, np.int32),
+                pilots=np.asarray(pilots, np.int32), carriers=np.asarray(carriers, np.int32))
+
+
+# ---------------------------------------------------------------- stub TF
+class _NumpyKerasModel:
+    """Keras-like model: Dense(relu)->BN->Dense(relu)->BN->Dense(linear), float64."""
+
+    def __init__(self, seed, d_in, hidden, d_out):
+        rng = np.random.default_rng(seed)
+        dims = [d_in] + list(hidden) + [d_out]
+        self.layers_ = []
+        for i in range(len(dims) - 1):
+            lim = np.sqrt(6.0 / (dims[i] + dims[i + 1]))
+            L = dict(W=rng.uniform(-lim, lim, (dims[i], dims[i + 1])),
+                     b=rng.uniform(-0.1, 0.1, dims[i + 1]))
+            if i < len(dims) - 2:
+                n = dims[i + 1]
+                L["bn"] = (rng.uniform(0.5, 1.5, n), rng.uniform(-0.1, 0.1, n),
+                           rng.uniform(-0.1, 0.1, n), rng.uniform(0.5, 1.5, n))
+            self.layers_.append(L)
+
+    def predict(self, x, batch_size=None):
+        h = np.asarray(x, np.float64)
+        for i, L in enumerate(self.layers_):
+            h = h @ L["W"] + L["b"]
+            if i < len(self.layers_) - 1:
+                h = np.maximum(h, 0.0)
+                g, be, mu, var = L["bn"]
+                h = g * (h - mu) / np.sqrt(var + 1e-3) + be
+        return h
+
+    def summary(self):
+        pass
+
+
+def install_stub_tf(model_factory):
+    tf = types.ModuleType("tensorflow")
+    keras = types.ModuleType("tensorflow.keras")
+    models = types.ModuleType("tensorflow.keras.models")
+    utils = types.ModuleType("tensorflow.keras.utils")
+    models.load_model = model_factory
+    utils.Sequence = object
+    keras.models = models
+    keras.utils = utils
+    tf.keras = keras
+    sys.modules.update({"tensorflow": tf, "tensorflow.keras": keras,
+                        "tensorflow.keras.models": models, "tensorflow.keras.utils": utils})
+
+
+def flatten_layers(prefix, layers, out):
+    for i, L in enumerate(layers):
+        out["%s_W%d" % (prefix, i)] = L["W"]
+        out["%s_b%d" % (prefix, i)] = L["b"]
+        if "bn" in L:
+            for nm, t in zip(("gamma", "beta", "mean", "var"), L["bn"]):
+                out["%s_bn%d_%s" % (prefix, i, nm)] = t
+
+
+# ---------------------------------------------------------------- 2. inference.py
+def run_inference_py():
+    d_in, hidden, d_out = 52, (48, 40), 52
+    nets = {"real": _NumpyKerasModel(6701, d_in, hidden, d_out),
+            "imag": _NumpyKerasModel(6702, d_in, hidden, d_out)}
+
+    def load_model(path):
+        return nets["real"] if os.path.basename(path).startswith("real") else nets["imag"]
+
+    install_stub_tf(load_model)
+    sys.path.insert(0, REF)
+    import inference as ref_inference                      # the unmodified reference file
+    pred = ref_inference.CSIPredictor("/nonexistent/model_dir")
+    rng = np.random.default_rng(67)
+    X = (rng.standard_normal((9, d_in)) + 1j * rng.standard_normal((9, d_in))).astype(np.complex128)
+    Y = pred.inference(X)
+    out = dict(X=X, Y=Y)
+    flatten_layers("real", nets["real"].layers_, out)
+    flatten_layers("imag", nets["imag"].layers_, out)
+    return out
+
+
+# ---------------------------------------------------------------- 3. DataGenerator
+def run_data_generator():
+    sys.path.insert(0, REF)
+    import massiveMIMO_dataGenerator as ref_dg             # unmodified reference file
+    n_pkt, n_rx, n_tx, len_ltf, nsc = 3, 2, 4, 24, 10
+    rng = np.random.default_rng(67)
+    ltf = rng.standard_normal((n_pkt, n_rx, len_ltf)) + 1j * rng.standard_normal((n_pkt, n_rx, len_ltf))
+    P = rng.choice([-1.0, 1.0], size=(n_tx, n_tx))
+    y = rng.standard_normal((n_pkt * n_rx * n_tx, nsc)) + 1j * rng.standard_normal((n_pkt * n_rx * n_tx, nsc))
+    X = np.zeros((n_pkt * n_rx * n_tx, 2), dtype=np.int64)
+    LTF = {}
+    for p in range(n_pkt):
+        for irx in range(n_rx):
+            h = 1000 + p * n_rx + irx                       # stands in for the random 32-bit hash (:52-59)
+            LTF[h] = {"real": ltf[p, irx].real.copy(), "imag": ltf[p, irx].imag.copy()}
+            for itx in range(n_tx):
+                samp_ix = p * (n_rx * n_tx) + irx * n_tx + itx   # create_..._dataset.py:62
+                X[samp_ix] = [h, itx]
+    dataset = {"X": X, "LTF": LTF, "P": P, "y": {"real": y.real.copy(), "imag": y.imag.copy()}}
+    prm = {"lenLTF": len_ltf, "nTX": n_tx, "nRX": n_rx, "nSubCarr": nsc}
+    out = dict(ltf=ltf, P=P, y=y, n_pkt=n_pkt, n_rx=n_rx, n_tx=n_tx)
+    for d in ("real", "imag"):
+        gen = ref_dg.DataGenerator(list(range(X.shape[0])), dataset, d, prm,
+                                   datasource="matlab_maMimo", method="default", batch_size=n_tx * n_rx)
+        gen.reorder_indexes()                               # test-mode order, ..._DNN.py:337
+        xs, xp, ys = [], [], []
+        for b in range(len(gen)):
+            (Xsig, Xp), yb, _ = gen[b]
+            xs.append(Xsig[:, :, 0]); xp.append(Xp); ys.append(yb)
+        out["Xsig_" + d] = np.concatenate(xs); out["Xp_" + d] = np.concatenate(xp)
+        out["y_" + d] = np.concatenate(ys)
+    return out
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, "ref_tables.npz"), **parse_tables())
+    np.savez_compressed(os.path.join(HERE, "ref_inference_py.npz"), **run_inference_py())
+    np.savez_compressed(os.path.join(HERE, "ref_data_generator.npz"), **run_data_generator())
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
