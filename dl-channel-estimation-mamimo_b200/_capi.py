@@ -26,7 +26,8 @@ class Config(C.Structure):
         ("d_in", C.c_int32), ("d_out", C.c_int32), ("n_hidden", C.c_int32),
         ("hidden", C.c_int32 * MAX_HIDDEN),
         ("len_ltf", C.c_int32), ("max_pkts", C.c_int32), ("act_scale_log2", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("kb_per_chunk", C.c_int32), ("host_chunk_pkts", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

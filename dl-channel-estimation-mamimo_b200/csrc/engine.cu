@@ -64,6 +64,8 @@ struct mamimo_engine {
   int num_sms = 0;
   int rows_per_pkt = 0;
   int max_pkts = 0;
+  int host_chunk = 0;           // units per chunk of the host-buffer pipeline
+  int kb_per_chunk = 1;
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
@@ -218,7 +220,7 @@ template <int S, int NLTF, bool HAD>
 mamimo_status launch_ls_t(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
   const long long grid = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
-  const size_t smem = (static_cast<size_t>(a.n_tx) * (a.pil_per_tile + 3) + (HAD ? 0 : a.n_tx * a.n_ltf)) * sizeof(float2);
+  const size_t smem = (static_cast<size_t>(a.n_tx) * (a.pil_per_tile + 4) + (HAD ? 0 : a.n_tx * a.n_ltf)) * sizeof(float2);
   if (smem > 48 * 1024)
     CK(e, cudaFuncSetAttribute(ls_kernel<S, NLTF, HAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)));
@@ -271,7 +273,7 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
       const bool last = (l == e->n_layers - 1);
       FcArgs a;
       memset(&a, 0, sizeof(a));
-      a.M = n_rows; a.N = d.N; a.num_k_blocks = d.K / e->block_k;
+      a.M = n_rows; a.N = d.N; a.num_k_blocks = d.K / e->block_k; a.kb_per_chunk = e->kb_per_chunk;
       a.a_plane_rows = A.rows_alloc; a.b_plane_rows = d.w.rows_alloc;
       a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = last ? 0 : 1;
       a.flags = e->d_flags;
@@ -407,7 +409,9 @@ mamimo_status run_chunked(mamimo_engine* e, int64_t n_units, int64_t units_per_c
     }
     return MAMIMO_OK;
   }
-  // host buffers: double-buffered H2D -> compute -> D2H on three streams
+  // host buffers: double-buffered H2D -> compute -> D2H on three streams, in small chunks so the
+  // three stages of neighbouring chunks overlap (PCIe is full duplex)
+  units_per_chunk = std::min<int64_t>(units_per_chunk, e->host_chunk);
   const int64_t cu = std::min(units_per_chunk, n_units);
   mamimo_status s = ensure_staging(e, cu * in0_unit_bytes, in1 ? cu * in1_unit_bytes : 0, hr ? cu * h_unit_bytes : 0,
                                    hls ? cu * hls_unit_bytes : 0);
@@ -571,6 +575,11 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   // chunking: ~64K rows per chunk by default
   int rows_per_unit = cfg->input_mode == MAMIMO_INPUT_PLANES ? 1 : e->rows_per_pkt;
   e->max_pkts = cfg->max_pkts > 0 ? cfg->max_pkts : std::max(1, 65536 / rows_per_unit);
+  // host pipeline granularity: ~8K rows per chunk so H2D, compute and D2H of neighbouring chunks overlap
+  e->host_chunk = cfg->host_chunk_pkts > 0 ? std::min(cfg->host_chunk_pkts, e->max_pkts)
+                                           : std::min(e->max_pkts, std::max(1, 8192 / rows_per_unit));
+  e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 1;
+  if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
   if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }
   e->rows_alloc = round_up(static_cast<int>(rows), 128);
@@ -747,6 +756,8 @@ mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y
   if (n_pkt < 0 || (n_pkt > 0 && (!Y || !H_ls))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
   if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
   if (y_mem != h_mem) return fail(e, MAMIMO_ERR_INVALID, "Y and H_ls must live in the same memory kind");
+  if ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(H_ls)) & 15)
+    return fail(e, MAMIMO_ERR_INVALID, "Y and H_ls must be 16-byte aligned");
   CK(e, cudaSetDevice(e->cfg.device));
   const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
   const size_t hb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_tx * e->cfg.n_sc * (h_type == MAMIMO_C128 ? 16 : 8);
@@ -764,6 +775,9 @@ mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_ty
   if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
   if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
   if (n_pkt < 0 || (n_pkt > 0 && (!Y || !H_real || !H_imag))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(H_ls) | reinterpret_cast<uintptr_t>(H_real) |
+       reinterpret_cast<uintptr_t>(H_imag)) & 15)
+    return fail(e, MAMIMO_ERR_INVALID, "Y, H_ls, H_real and H_imag must be 16-byte aligned");
   CK(e, cudaSetDevice(e->cfg.device));
   const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
   const size_t hlsb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.n_sc * 8;

@@ -12,6 +12,14 @@
 //
 // Both K-major: A = activations [rows][Kpad], W = weights [N][Kpad] (the transpose of the
 // Keras kernel), so each output element is a dot product of two contiguous rows.
+//
+// Accuracy note (measured on B200, round 1): the tensor core adds every MMA's result into the
+// TMEM accumulator with truncation (round toward zero).  A 1024-deep layer is 64..128 k-steps x 3
+// passes = 192..384 truncations of a full-magnitude accumulator, a systematic shrink of ~2e-5 --
+// outside the 1e-5 budget.  So the accumulation chain is cut: the MMA warp accumulates only
+// `kb_per_chunk` k-blocks into one TMEM buffer (correction passes first, while the buffer is still
+// small, the dominant hi.hi pass last), the epilogue warps drain that buffer into FP32 registers
+// with round-to-nearest adds while the MMA warp fills the other buffer.
 #pragma once
 #include "ptx.cuh"
 #include "schemes.cuh"
@@ -22,6 +30,7 @@ struct FcArgs {
   int M;                 // valid rows
   int N;                 // valid output features
   int num_k_blocks;      // Kpad / kBlockK
+  int kb_per_chunk;      // k-blocks accumulated inside the tensor core before a register drain
   int a_plane_rows;      // rows_alloc of the A operand (plane stride, rows)
   int b_plane_rows;      // Npad of the W operand
   const float* bias;     // [N], BN-folded
@@ -43,7 +52,10 @@ struct FcArgs {
 };
 
 constexpr int kFcBlockM = 128;
-constexpr int kFcThreads = 192;          // warp0 TMA, warp1 MMA+TMEM, warps2-5 epilogue
+// warpgroup 0: warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2-3 idle (donate registers)
+// warpgroups 1-2: 8 epilogue warps; warp w drains TMEM lane quarter (w & 3), column half ((w - 4) >> 2)
+constexpr int kFcThreads = 384;
+constexpr int kFcEpiThreads = 256;
 constexpr int kFcSmemBytes = 227 * 1024;
 
 template <int S, int BN>
@@ -56,26 +68,28 @@ struct FcTcCfg {
   static constexpr int kStagesRaw = (kFcSmemBytes - 1024 - kAuxBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;                   // double-buffered accumulator
+  static constexpr int kColsPerThread = BN / 2;              // each epilogue thread: one row, half the columns
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
   static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "power-of-two TMEM allocation");
+  static_assert(kColsPerThread % 32 == 0, "drain granularity is 32 columns");
 };
 
-// One 32-column chunk of one row: bias, activation, then either split planes or float32.
+// One 32-column group of one row: bias, activation, then either split planes or float32.
 template <int S>
-__device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const uint32_t (&r)[32], const float* sbias,
+__device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const float (&acc)[32], const float* sbias,
                                                   int row, int n0, bool& ovf) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float x = fmaf(__uint_as_float(r[j]), a.alpha, sbias[j]);
+    float x = fmaf(acc[j], a.alpha, sbias[j]);
     if (a.relu) x = fmaxf(x, 0.0f);
     v[j] = x;
   }
   if (a.out_planes) {
     if (n0 >= a.out_kpad) return;
-    constexpr int kWords = 32 * sizeof(E) / 4;            // 32-bit words per plane per chunk
+    constexpr int kWords = 32 * sizeof(E) / 4;            // 32-bit words per plane per group
     uint32_t pk[Sch::kPlanes][kWords];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
@@ -125,6 +139,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   using Sch = Scheme<S>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kPlanes = Sch::kPlanes;
+  constexpr int kGroups = Cfg::kColsPerThread / 32;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,6 +157,8 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int m_tiles = (a.M + kFcBlockM - 1) / kFcBlockM;
   const int n_tiles = (a.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
+  const int kbc = a.kb_per_chunk;
+  const int n_chunks = (a.num_k_blocks + kbc - 1) / kbc;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -150,7 +167,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + s, 1);
-      mbar_init(tempty_bar + s, 4);       // one arrive per epilogue warp
+      mbar_init(tempty_bar + s, kFcEpiThreads / 32);   // one arrive per epilogue warp
     }
     *cta_abort = 0;
     fence_barrier_init();
@@ -166,94 +183,124 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < a.num_k_blocks; ++kb) {
-          if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ================= TMA producer =================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+          const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+          for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+            if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
 #pragma unroll
-          for (int p = 0; p < kPlanes; ++p)
-            tma_load_2d(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
-                        p * a.a_plane_rows + m_blk * kFcBlockM);
+            for (int p = 0; p < kPlanes; ++p)
+              tma_load_2d(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
+                          p * a.a_plane_rows + m_blk * kFcBlockM);
 #pragma unroll
-          for (int p = 0; p < kPlanes; ++p)
-            tma_load_2d(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,
-                        kb * Sch::kBlockK, p * a.b_plane_rows + n_blk * BN);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int p = 0; p < kPlanes; ++p)
+              tma_load_2d(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,
+                          kb * Sch::kBlockK, p * a.b_plane_rows + n_blk * BN);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(Sch::kFmt, kFcBlockM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) break;
-        tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.num_k_blocks; ++kb) {
-          if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kPlanes * Cfg::kABytes;
+    } else if (warp == 1) {
+      // ================= MMA issuer (one thread) =================
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc(Sch::kFmt, kFcBlockM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        uint32_t unit = 0;                            // one unit = one (tile, k-chunk) accumulation
+        for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+          for (int c = 0; c < n_chunks && ok; ++c, ++unit) {
+            const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+            if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            const int kb_end = min(a.num_k_blocks, (c + 1) * kbc);
+            uint32_t fresh = 1;                       // first MMA of the unit overwrites the buffer
+            for (int kb = c * kbc; kb < kb_end; ++kb) {
+              if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
+              tc_fence_after_sync();
+              const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+              const uint32_t sb = sa + kPlanes * Cfg::kABytes;
+              // correction passes (hi.lo, lo.hi) first: they land while the accumulator is small, so the
+              // tensor core's truncating add costs nothing; the dominant hi.hi pass closes the k-block
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {          // 4 k-steps of 32 bytes inside the 128-byte swizzle row
+              for (int ps = Sch::kPasses - 1; ps >= 0; --ps) {
 #pragma unroll
-            for (int ps = 0; ps < Sch::kPasses; ++ps) {
-              const uint64_t da = umma_desc_sw128(sa + pass_a(ps) * Cfg::kABytes + ks * 32);
-              const uint64_t db = umma_desc_sw128(sb + pass_b(ps) * Cfg::kBBytes + ks * 32);
-              umma_ss<Sch::kTf32>(tmem_d, da, db, idesc, (kb | ks | ps) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks) {      // 4 k-steps of 32 bytes inside the 128-byte swizzle row
+                  const uint64_t da = umma_desc_sw128(sa + pass_a(ps) * Cfg::kABytes + ks * 32);
+                  const uint64_t db = umma_desc_sw128(sb + pass_b(ps) * Cfg::kBBytes + ks * 32);
+                  umma_ss<Sch::kTf32>(tmem_d, da, db, idesc, fresh ? 0u : 1u);
+                  fresh = 0;
+                }
+              }
+              umma_commit(empty_bar + stage);         // smem slot reusable once these MMAs retire
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (ok) umma_commit(tfull_bar + acc);     // chunk accumulated -> epilogue may drain it
           }
-          umma_commit(empty_bar + stage);           // smem slot reusable once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (ok) umma_commit(tfull_bar + acc);       // accumulator complete -> epilogue
       }
     }
   } else {
-    // ================= epilogue warps (TMEM -> regs -> global) =================
+    // ================= epilogue warps (TMEM -> FP32 registers (RN) -> global) =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - 4;                        // 0..7
     const int q = warp & 3;                         // TMEM lane quarter this warp may touch
-    const int et = (warp - 2) * 32 + lane;          // 0..127 among epilogue threads
+    const int half = ew >> 2;                       // column half
+    const int et = ew * 32 + lane;                  // 0..255 among epilogue threads
     bool ovf = false;
+    uint32_t unit = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      float* sb = sbias + acc * BN;
-      for (int i = et; i < BN; i += 128) {
+      float* sb = sbias + (it & 1) * BN;
+      for (int i = et; i < BN; i += kFcEpiThreads) {
         const int n = n_blk * BN + i;
         sb[i] = (n < a.N) ? __ldg(a.bias + n) : 0.0f;
       }
-      named_bar_sync(1, 128);
-      if (!mbar_wait(tfull_bar + acc, acc_phase, cta_abort, a.flags)) break;
-      tc_fence_after_sync();
-      const int row = m_blk * kFcBlockM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (row < a.M) fc_epilogue_chunk<S>(a, r, sb + c * 32, row, n_blk * BN + c * 32, ovf);
+      named_bar_sync(1, kFcEpiThreads);
+      float sum[kGroups][32];
+      for (int c = 0; c < n_chunks; ++c, ++unit) {
+        const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+        if (!mbar_wait(tfull_bar + acc, acc_phase, cta_abort, a.flags)) { ok = false; break; }
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * Cfg::kColsPerThread;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          uint32_t r[32];
+          tmem_ld32(taddr + g * 32, r);
+          tmem_ld_wait();
+          if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[g][j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[g][j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + acc);   // buffer free: MMA warp may start the next chunk
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (!ok) break;
+      const int row = m_blk * kFcBlockM + q * 32 + lane;
+      if (row < a.M) {
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          const int col = half * Cfg::kColsPerThread + g * 32;
+          fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+        }
+      }
     }
     if (ovf) atomicOr(a.flags, kFlagRange);
   }

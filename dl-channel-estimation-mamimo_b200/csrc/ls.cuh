@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
   int hi = min(pil0 + a.pil_per_tile, a.n_pil);
   if (a.n_ps > 1 && hi < a.n_pil) hi += 1;
   const int n_hold = hi - lo;
-  const int pitch = a.pil_per_tile + 3;                 // odd pitch: conflict-free column sweeps
+  const int pitch = a.pil_per_tile + 4;                 // even pitch: rows stay 16-byte aligned for float4 reads
   float2* sh = sm_ls;                                   // [n_tx][pitch]
   float2* sP = sm_ls + static_cast<size_t>(a.n_tx) * pitch;   // dense path: [n_tx][n_ltf]
 
@@ -135,36 +135,87 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
   const int k1 = (pil0 + a.pil_per_tile >= a.n_pil) ? a.n_sc : min(a.n_sc, (pil0 + a.pil_per_tile) * a.n_ps);
   const int nk = k1 - k0;
   bool ovf = false;
-  const float inv_nps = 1.0f / static_cast<float>(a.n_ps);
-  for (int idx = threadIdx.x; idx < a.n_tx * nk; idx += blockDim.x) {
-    const int j = idx / nk;
-    const int k = k0 + (idx - j * nk);
-    float2 h;
-    if (a.n_ps == 1) {
-      h = sh[j * pitch + (k - k0)];
-    } else if (a.n_pil == 1) {
-      h = sh[j * pitch];
-    } else {
-      const int seg = min(k / a.n_ps, a.n_pil - 2);
-      const float w = static_cast<float>(k - seg * a.n_ps) * inv_nps;
-      const float2 h0 = sh[j * pitch + (seg - lo)];
-      const float2 h1 = sh[j * pitch + (seg + 1 - lo)];
-      h = make_float2(h0.x + w * (h1.x - h0.x), h0.y + w * (h1.y - h0.y));
-    }
-    const size_t row = static_cast<size_t>(prx) * a.n_tx + j;
-    if (a.H_ls) {
-      if (a.h_double) reinterpret_cast<double2*>(a.H_ls)[row * a.n_sc + k] = make_double2(h.x, h.y);
-      else reinterpret_cast<float2*>(a.H_ls)[row * a.n_sc + k] = h;
-    }
-    if (a.planes[0]) {
-      E pr[Sch::kPlanes], pi[Sch::kPlanes];
-      Sch::split(h.x, a.scale, pr, &ovf);
-      Sch::split(h.y, a.scale, pi, &ovf);
+  const size_t row0 = static_cast<size_t>(prx) * a.n_tx;
+  if (a.n_ps == 1 && (nk & 3) == 0 && (a.n_sc & 3) == 0 && (a.kpad & 3) == 0) {
+    // fast path (every reference call site): 4 consecutive tones per thread, 8/16/32-byte stores
+    const int nq = nk >> 2;
+    for (int idx = threadIdx.x; idx < a.n_tx * nq; idx += blockDim.x) {
+      const int j = idx / nq;
+      const int kk = (idx - j * nq) << 2;
+      const float4 v01 = *reinterpret_cast<const float4*>(sh + j * pitch + kk);
+      const float4 v23 = *reinterpret_cast<const float4*>(sh + j * pitch + kk + 2);
+      const float re[4] = {v01.x, v01.z, v23.x, v23.z};
+      const float im[4] = {v01.y, v01.w, v23.y, v23.w};
+      const size_t row = row0 + j;
+      const int k = k0 + kk;
+      if (a.H_ls) {
+        if (a.h_double) {
+          double2* d = reinterpret_cast<double2*>(a.H_ls) + row * a.n_sc + k;
 #pragma unroll
-      for (int pl = 0; pl < Sch::kPlanes; ++pl) {
-        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
-        reinterpret_cast<E*>(a.planes[0])[off] = pr[pl];
-        reinterpret_cast<E*>(a.planes[1])[off] = pi[pl];
+          for (int i = 0; i < 4; ++i) d[i] = make_double2(re[i], im[i]);
+        } else {
+          float4* d = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.H_ls) + row * a.n_sc + k);
+          d[0] = v01;
+          d[1] = v23;
+        }
+      }
+      if (a.planes[0]) {
+        E pr[4][Sch::kPlanes], pi[4][Sch::kPlanes];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          Sch::split(re[i], a.scale, pr[i], &ovf);
+          Sch::split(im[i], a.scale, pi[i], &ovf);
+        }
+#pragma unroll
+        for (int pl = 0; pl < Sch::kPlanes; ++pl) {
+          const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+          E* d0 = reinterpret_cast<E*>(a.planes[0]) + off;
+          E* d1 = reinterpret_cast<E*>(a.planes[1]) + off;
+          if constexpr (sizeof(E) == 4) {
+            *reinterpret_cast<float4*>(d0) = make_float4(pr[0][pl], pr[1][pl], pr[2][pl], pr[3][pl]);
+            *reinterpret_cast<float4*>(d1) = make_float4(pi[0][pl], pi[1][pl], pi[2][pl], pi[3][pl]);
+          } else {
+            auto bits = [](E x) { return static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&x)); };
+            *reinterpret_cast<uint2*>(d0) = make_uint2(bits(pr[0][pl]) | (bits(pr[1][pl]) << 16),
+                                                       bits(pr[2][pl]) | (bits(pr[3][pl]) << 16));
+            *reinterpret_cast<uint2*>(d1) = make_uint2(bits(pi[0][pl]) | (bits(pi[1][pl]) << 16),
+                                                       bits(pi[2][pl]) | (bits(pi[3][pl]) << 16));
+          }
+        }
+      }
+    }
+  } else {
+    const float inv_nps = 1.0f / static_cast<float>(a.n_ps);
+    for (int idx = threadIdx.x; idx < a.n_tx * nk; idx += blockDim.x) {
+      const int j = idx / nk;
+      const int k = k0 + (idx - j * nk);
+      float2 h;
+      if (a.n_ps == 1) {
+        h = sh[j * pitch + (k - k0)];
+      } else if (a.n_pil == 1) {
+        h = sh[j * pitch];
+      } else {
+        const int seg = min(k / a.n_ps, a.n_pil - 2);
+        const float w = static_cast<float>(k - seg * a.n_ps) * inv_nps;
+        const float2 h0 = sh[j * pitch + (seg - lo)];
+        const float2 h1 = sh[j * pitch + (seg + 1 - lo)];
+        h = make_float2(h0.x + w * (h1.x - h0.x), h0.y + w * (h1.y - h0.y));
+      }
+      const size_t row = row0 + j;
+      if (a.H_ls) {
+        if (a.h_double) reinterpret_cast<double2*>(a.H_ls)[row * a.n_sc + k] = make_double2(h.x, h.y);
+        else reinterpret_cast<float2*>(a.H_ls)[row * a.n_sc + k] = h;
+      }
+      if (a.planes[0]) {
+        E pr[Sch::kPlanes], pi[Sch::kPlanes];
+        Sch::split(h.x, a.scale, pr, &ovf);
+        Sch::split(h.y, a.scale, pi, &ovf);
+#pragma unroll
+        for (int pl = 0; pl < Sch::kPlanes; ++pl) {
+          const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+          reinterpret_cast<E*>(a.planes[0])[off] = pr[pl];
+          reinterpret_cast<E*>(a.planes[1])[off] = pi[pl];
+        }
       }
     }
   }
