@@ -314,7 +314,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MAMIMO_BENCH_PRECISION", "tf32x3"),
+    ap.add_argument("--precision", default=os.environ.get("MAMIMO_BENCH_PRECISION", "fp16x3"),
                     choices=["tf32x3", "fp16x3", "bf16x1", "fp32_simt"])
     ap.add_argument("--npkt", type=int, default=500)
     ap.add_argument("--gen-pkts", type=int, default=125, help="distinct synthetic packets generated (tiled to npkt)")

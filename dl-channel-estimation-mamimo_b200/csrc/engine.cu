@@ -65,7 +65,7 @@ struct mamimo_engine {
   int rows_per_pkt = 0;
   int max_pkts = 0;
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
-  int kb_per_chunk = 1;
+  int kb_per_chunk = 2;
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
@@ -578,7 +578,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   // host pipeline granularity: ~8K rows per chunk so H2D, compute and D2H of neighbouring chunks overlap
   e->host_chunk = cfg->host_chunk_pkts > 0 ? std::min(cfg->host_chunk_pkts, e->max_pkts)
                                            : std::min(e->max_pkts, std::max(1, 8192 / rows_per_unit));
-  e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 1;
+  e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 2;
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
   if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }

@@ -90,7 +90,7 @@ typedef struct {
   int32_t len_ltf;          /* mode A only: time-domain samples per (pkt,rx) fed to the net */
   int32_t max_pkts;         /* packets per internal chunk (workspace sizing); 0 = default */
   int32_t act_scale_log2;   /* FP16X3 only: power-of-two operand scale (default 6) */
-  int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (1) */
+  int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (2) */
   int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default */
   int32_t reserved[5];
 } mamimo_config;
