@@ -27,7 +27,8 @@ class Config(C.Structure):
         ("hidden", C.c_int32 * MAX_HIDDEN),
         ("len_ltf", C.c_int32), ("max_pkts", C.c_int32), ("act_scale_log2", C.c_int32),
         ("kb_per_chunk", C.c_int32), ("host_chunk_pkts", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("fc_single_cta", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -32,7 +32,8 @@ struct DevLayer {
   float* bias = nullptr;   // [N]
   int N = 0, K = 0;
   float w_scale = 1.f;
-  CUtensorMap tmap_b;
+  CUtensorMap tmap_b;       // box of 256 weight rows (1-CTA kernel)
+  CUtensorMap tmap_b_half;  // box of 128 weight rows (CTA-pair kernel: each CTA stages half the tile)
   CUtensorMap tmap_a;      // A operand of this layer (net-specific buffer for layer 0)
 };
 
@@ -66,6 +67,7 @@ struct mamimo_engine {
   int max_pkts = 0;
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 2;
+  bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
@@ -175,6 +177,9 @@ mamimo_status set_tc_attr(mamimo_engine* e) {
   using Cfg = FcTcCfg<S, kTcBN>;
   const int smem = Cfg::kStages * Cfg::kStageBytes + Cfg::kAuxBytes + 1024;
   CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  using Cfg2 = FcTc2Cfg<S>;
+  const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
+  CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   return MAMIMO_OK;
 }
 
@@ -252,6 +257,16 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
     const int grid = ((a.M + 127) / 128) * ((a.N + 127) / 128);
     fc_simt_kernel<S><<<grid, 256, 0, st>>>(a);
   } else {
+    if (e->fc_pair) {
+      using Cfg2 = FcTc2Cfg<S>;
+      const int pair_tiles = ((a.M + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((a.N + kTcBN - 1) / kTcBN);
+      const int grid2 = 2 * std::min(pair_tiles, e->num_sms / 2);
+      const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
+      fc_tc2_kernel<S><<<grid2, kFcThreads, smem2, st>>>(d.tmap_a, d.tmap_b_half, a);
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches++;
+      return MAMIMO_OK;
+    }
     using Cfg = FcTcCfg<S, kTcBN>;
     const int tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcBN - 1) / kTcBN);
     const int grid = std::min(tiles, e->num_sms);
@@ -580,9 +595,11 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
                                            : std::min(e->max_pkts, std::max(1, 8192 / rows_per_unit));
   e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 2;
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
+  e->fc_pair = cfg->fc_single_cta == 0;
+  if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
   if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }
-  e->rows_alloc = round_up(static_cast<int>(rows), 128);
+  e->rows_alloc = round_up(static_cast<int>(rows), 256);   // whole CTA-pair row tiles
 
   auto ck = [&](cudaError_t ce, const char* what) { if (ce != cudaSuccess && s == MAMIMO_OK) s = fail_cuda(e, ce, what); };
   ck(cudaMalloc(&e->d_flags, sizeof(uint32_t)), "cudaMalloc flags");
@@ -739,6 +756,8 @@ mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
       if (s != MAMIMO_OK) return s;
       if (e->cfg.precision != MAMIMO_PREC_FP32_SIMT) {
         s = make_map(e, &d.tmap_b, d.w, d.w.kpad, kTcBN);
+        if (s != MAMIMO_OK) return s;
+        s = make_map(e, &d.tmap_b_half, d.w, d.w.kpad, kTcBN / 2);
         if (s != MAMIMO_OK) return s;
         const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
         s = make_map(e, &d.tmap_a, A, d.K, kFcBlockM);

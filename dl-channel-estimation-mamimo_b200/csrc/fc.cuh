@@ -312,6 +312,213 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 output tile.
+// Each CTA stages its own 128 activation rows and HALF of the weight tile (128 of the 256 output
+// features); one tcgen05.mma issued by the leader CTA reads both shared memories, so the weight bytes
+// each SM pulls from L2 are halved (the 1-CTA kernel is L2->SMEM bound: 62 B/clk/SM vs 42 here) and a
+// third pipeline stage fits.  Each CTA keeps the accumulator of its own 128 rows in its own TMEM and
+// drains / stores it exactly like the 1-CTA kernel.
+template <int S>
+struct FcTc2Cfg {
+  using Sch = Scheme<S>;
+  static constexpr int BN = 256;
+  static constexpr int kABytes = kFcBlockM * 128;            // 128 rows x 128 B (this CTA's rows)
+  static constexpr int kBBytes = (BN / 2) * 128;             // this CTA's half of the weight tile
+  static constexpr int kStageBytes = Sch::kPlanes * (kABytes + kBBytes);
+  static constexpr int kAuxBytes = 2048 + 2 * BN * 4;
+  static constexpr int kStagesRaw = (kFcSmemBytes - 1024 - kAuxBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kColsPerThread = BN / 2;
+  static_assert(kStages >= 2, "need at least a double-buffered operand ring");
+};
+
+template <int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFcThreads, 1)
+fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const FcArgs a) {
+  using Cfg = FcTc2Cfg<S>;
+  using Sch = Scheme<S>;
+  constexpr int BN = Cfg::BN;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kPlanes = Sch::kPlanes;
+  constexpr int kGroups = Cfg::kColsPerThread / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aux = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [kStages]  (leader's copy is the live one)
+  uint64_t* empty_bar = full_bar + kStages;                         // [kStages]  per CTA, multicast-committed
+  uint64_t* tfull_bar = empty_bar + kStages;                        // [2]        per CTA, multicast-committed
+  uint64_t* tempty_bar = tfull_bar + 2;                             // [2]        (leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* cta_abort = tmem_slot + 1;
+  float* sbias = reinterpret_cast<float*>(aux + 2048);              // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int m_pairs = (a.M + 2 * kFcBlockM - 1) / (2 * kFcBlockM);
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const int total_tiles = m_pairs * n_tiles;
+  const int kbc = a.kb_per_chunk;
+  const int n_chunks = (a.num_k_blocks + kbc - 1) / kbc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);                      // leader's arrive.expect_tx; bytes from both CTAs
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + s, 1);
+      mbar_init(tempty_bar + s, 2 * (kFcEpiThreads / 32));   // epilogue warps of BOTH CTAs
+    }
+    *cta_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();                                  // barriers of both CTAs initialised before any remote use
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ================= TMA producer (both CTAs) =================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
+          const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+          const int row0 = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM;        // this CTA's activation rows
+          const int wrow0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);           // this CTA's weight rows
+          for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+            if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p)
+              tma_load_2d_pair(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
+                               p * a.a_plane_rows + row0);
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p)
+              tma_load_2d_pair(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,
+                               kb * Sch::kBlockK, p * a.b_plane_rows + wrow0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ================= MMA issuer (one thread of the leader CTA) =================
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc(Sch::kFmt, 2 * kFcBlockM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        uint32_t unit = 0;
+        for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
+          for (int c = 0; c < n_chunks && ok; ++c, ++unit) {
+            const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+            if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            const int kb_end = min(a.num_k_blocks, (c + 1) * kbc);
+            uint32_t fresh = 1;
+            for (int kb = c * kbc; kb < kb_end; ++kb) {
+              if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
+              tc_fence_after_sync();
+              const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+              const uint32_t sb = sa + kPlanes * Cfg::kABytes;
+#pragma unroll
+              for (int ps = Sch::kPasses - 1; ps >= 0; --ps) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t da = umma_desc_sw128(sa + pass_a(ps) * Cfg::kABytes + ks * 32);
+                  const uint64_t db = umma_desc_sw128(sb + pass_b(ps) * Cfg::kBBytes + ks * 32);
+                  umma_ss_pair<Sch::kTf32>(tmem_d, da, db, idesc, fresh ? 0u : 1u);
+                  fresh = 0;
+                }
+              }
+              umma_commit_pair(empty_bar + stage, 3);   // frees this stage in both CTAs
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (ok) umma_commit_pair(tfull_bar + acc, 3);   // both CTAs' epilogues may drain
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (each CTA drains its own 128 rows) =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int et = ew * 32 + lane;
+    bool ovf = false;
+    uint32_t unit = 0;
+    int it = 0;
+    bool ok = true;
+    for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters, ++it) {
+      const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
+      float* sb = sbias + (it & 1) * BN;
+      for (int i = et; i < BN; i += kFcEpiThreads) {
+        const int n = n_blk * BN + i;
+        sb[i] = (n < a.N) ? __ldg(a.bias + n) : 0.0f;
+      }
+      named_bar_sync(1, kFcEpiThreads);
+      float sum[kGroups][32];
+      for (int c = 0; c < n_chunks; ++c, ++unit) {
+        const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+        if (!mbar_wait(tfull_bar + acc, acc_phase, cta_abort, a.flags)) { ok = false; break; }
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * Cfg::kColsPerThread;
+#pragma unroll
+        for (int g = 0; g < kGroups; g += 2) {
+          uint32_t r[64];
+          tmem_ld64(taddr + g * 32, r);
+          tmem_ld_wait();
+          if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar + acc);
+      }
+      if (!ok) break;
+      const int row = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM + q * 32 + lane;
+      if (row < a.M) {
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          const int col = half * Cfg::kColsPerThread + g * 32;
+          fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+        }
+      }
+    }
+    if (ovf) atomicOr(a.flags, kFlagRange);
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();                                  // neither CTA may exit while its pair can still touch it
+  tc_fence_after_sync();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact FP32 CUDA-core GEMM: 128x128 tile, 256 threads, 8x8 micro-tile, BK = 16.
 // A [rows_alloc][kpad] and W [Npad][kpad] are both K-major and zero padded, so no K masking.
 template <int S>

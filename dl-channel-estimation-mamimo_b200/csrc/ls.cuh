@@ -95,12 +95,31 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
     const int k = pil * a.n_ps;
     const float2 inv = __ldg(a.inv_den + pil);
     if constexpr (HAD) {
-      float2 v[NLTF];
+      // H_NLTF = H_NB (x) H_BLK: 16-point transforms in registers (keeps the kernel at <= 6 CTAs/SM worth
+      // of registers), the outer NB-point stage through this thread's own shared-memory column
+      constexpr int BLK = NLTF < 16 ? NLTF : 16;
+      constexpr int NB = NLTF / BLK;
+#pragma unroll 1
+      for (int b = 0; b < NB; ++b) {      // not unrolled: 16 loads in flight per thread, ~70 registers
+        float2 v[BLK];
 #pragma unroll
-      for (int n = 0; n < NLTF; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
-      fwht<NLTF>(v);
+        for (int n = 0; n < BLK; ++n)
+          v[n] = ld_y(a.Y, y_base + static_cast<size_t>(b * BLK + n) * a.n_sc + k, a.y_double);
+        fwht<BLK>(v);
 #pragma unroll
-      for (int j = 0; j < NLTF; ++j) sh[j * pitch + t] = cmul(v[j], inv);
+        for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * pitch + t] = (NB == 1) ? cmul(v[j], inv) : v[j];
+      }
+      if constexpr (NB > 1) {
+#pragma unroll 4
+        for (int j = 0; j < BLK; ++j) {
+          float2 u[NB];
+#pragma unroll
+          for (int b = 0; b < NB; ++b) u[b] = sh[(b * BLK + j) * pitch + t];
+          fwht<NB>(u);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) sh[(b * BLK + j) * pitch + t] = cmul(u[b], inv);
+        }
+      }
     } else if constexpr (NLTF > 0) {
       float2 v[NLTF];
 #pragma unroll

@@ -1,0 +1,137 @@
+// MATLAB MEX gateway over the C ABI (include/mamimo.h).  Thin: argument checks + pointer hand-off.
+//
+//   mamimo_mex('create', cfg)                      cfg: struct with n_tx n_rx n_sc [n_ltf n_ps hidden d_out precision]
+//   mamimo_mex('pilots', ltf_o, P)                 ltf_o = ltf(ind) [Nsc x 1] real, P [numSTS x nltf] real (helperGetP)
+//   mamimo_mex('load', net, layer, W, b [, gamma, beta, mean, var])   W single [in x out]' (Keras kernel, row-major)
+//   mamimo_mex('finalize')
+//   hD = mamimo_mex('ls', rxData)                  rxData complex double [Nsc x nltf x Nr (x Npkt)]
+//   [hD, Hr, Hi] = mamimo_mex('estimate', rxData)  Hr/Hi single [Nsc x Nt*Nr*Npkt] (column = pair row)
+//   ltf = mamimo_mex('ltf')                        256 x 1 tone table (no engine needed)
+//   mamimo_mex('destroy')
+//
+// 'ls' replaces the loop body of pg/helperMIMOChannelEstimate.m:33-36; the .m shim of the original name is in
+// matlab/helperMIMOChannelEstimate.m.  MATLAB's column-major [Nsc x nltf x Nr x Npkt] IS the engine's C-order
+// [Npkt][Nr][nltf][Nsc], so buffers are handed over without a copy (interleaved complex, -R2018a).
+// Errors follow the reference's error(message(...)) style through mexErrMsgIdAndTxt, which long-jumps:
+// nothing heap-allocated is live at those points, and the engine persists in a static freed by mexAtExit.
+#include <string.h>
+
+#include "mex.h"
+#include "mamimo.h"
+
+static mamimo_engine* g_engine = NULL;
+
+static void at_exit(void) {
+  if (g_engine) { mamimo_destroy(g_engine); g_engine = NULL; }
+}
+
+static void fail(mamimo_status s) {
+  if (s != MAMIMO_OK) mexErrMsgIdAndTxt("mamimo:engine", "%s: %s", mamimo_status_string(s), mamimo_last_error(g_engine));
+}
+
+static int field_int(const mxArray* st, const char* name, int dflt) {
+  const mxArray* f = mxGetField(st, 0, name);
+  return (f && !mxIsEmpty(f)) ? (int)mxGetScalar(f) : dflt;
+}
+
+static void need_engine(void) {
+  if (!g_engine) mexErrMsgIdAndTxt("mamimo:state", "call mamimo_mex('create', cfg) first");
+}
+
+// rxData dims -> n_pkt; checks [Nsc x nltf x Nr (x Npkt)] against the engine configuration
+static mwSize check_rx(const mxArray* rx, const mamimo_config* c) {
+  if (!mxIsComplex(rx) || !mxIsDouble(rx)) mexErrMsgIdAndTxt("mamimo:type", "rxData must be complex double");
+  const mwSize nd = mxGetNumberOfDimensions(rx);
+  const mwSize* d = mxGetDimensions(rx);
+  const mwSize nr = nd >= 3 ? d[2] : 1, np = nd >= 4 ? d[3] : 1;
+  if (nd > 4 || d[0] != (mwSize)c->n_sc || d[1] != (mwSize)c->n_ltf || nr != (mwSize)c->n_rx)
+    mexErrMsgIdAndTxt("mamimo:size", "rxData must be [Nsc x nltf x Nr (x Npkt)] = [%d x %d x %d]", c->n_sc, c->n_ltf, c->n_rx);
+  return np;
+}
+
+static mamimo_config g_cfg;
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("mamimo:usage", "first argument must be a command string");
+  char cmd[32];
+  {
+    char* s = mxArrayToString(prhs[0]);
+    strncpy(cmd, s ? s : "", sizeof(cmd) - 1);
+    cmd[sizeof(cmd) - 1] = 0;
+    mxFree(s);
+  }
+  if (!strcmp(cmd, "create")) {
+    if (nrhs < 2 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("mamimo:usage", "create needs a cfg struct");
+    at_exit();
+    mamimo_config_init(&g_cfg);
+    g_cfg.n_tx = field_int(prhs[1], "n_tx", 0);
+    g_cfg.n_rx = field_int(prhs[1], "n_rx", 0);
+    g_cfg.n_sc = field_int(prhs[1], "n_sc", 0);
+    g_cfg.n_ltf = field_int(prhs[1], "n_ltf", g_cfg.n_tx);
+    g_cfg.n_ps = field_int(prhs[1], "n_ps", 1);
+    g_cfg.precision = field_int(prhs[1], "precision", MAMIMO_PREC_TF32X3);
+    g_cfg.d_out = field_int(prhs[1], "d_out", 0);
+    g_cfg.d_in = g_cfg.d_out > 0 ? g_cfg.n_sc : 0;
+    const mxArray* h = mxGetField(prhs[1], 0, "hidden");
+    if (h && mxIsDouble(h)) {
+      g_cfg.n_hidden = (int)mxGetNumberOfElements(h);
+      if (g_cfg.n_hidden > MAMIMO_MAX_HIDDEN) mexErrMsgIdAndTxt("mamimo:size", "too many hidden layers");
+      for (int i = 0; i < g_cfg.n_hidden; ++i) g_cfg.hidden[i] = (int)mxGetDoubles(h)[i];
+    }
+    mamimo_status s = mamimo_create(&g_cfg, &g_engine);
+    if (s != MAMIMO_OK) mexErrMsgIdAndTxt("mamimo:engine", "%s: %s", mamimo_status_string(s), mamimo_last_error(NULL));
+    mexAtExit(at_exit);
+  } else if (!strcmp(cmd, "destroy")) {
+    at_exit();
+  } else if (!strcmp(cmd, "ltf")) {               // 256 x 1 VHT-LTF tone table (helperMIMOChannelEstimate.m:16-23)
+    int8_t t[256];
+    mamimo_vht_ltf256(t);
+    plhs[0] = mxCreateDoubleMatrix(256, 1, mxREAL);
+    for (int i = 0; i < 256; ++i) mxGetDoubles(plhs[0])[i] = t[i];
+  } else if (!strcmp(cmd, "pilots")) {
+    need_engine();
+    if (nrhs < 3 || !mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || mxIsComplex(prhs[1]) || mxIsComplex(prhs[2]))
+      mexErrMsgIdAndTxt("mamimo:usage", "pilots needs real double ltf_o and P");
+    const size_t np = mxGetNumberOfElements(prhs[1]), nP = mxGetNumberOfElements(prhs[2]);
+    if (nP != (size_t)g_cfg.n_tx * g_cfg.n_ltf) mexErrMsgIdAndTxt("mamimo:size", "P must be [numSTS x nltf]");
+    static float xp[2 * 65536], Pm[2 * 64 * 64];
+    if (np > 65536) mexErrMsgIdAndTxt("mamimo:size", "too many pilot tones");
+    for (size_t i = 0; i < np; ++i) { xp[2 * i] = (float)mxGetDoubles(prhs[1])[i]; xp[2 * i + 1] = 0.f; }
+    for (int j = 0; j < g_cfg.n_tx; ++j)            // MATLAB column-major P(j,n) -> row-major [tx][ltf]
+      for (int n = 0; n < g_cfg.n_ltf; ++n) {
+        Pm[2 * (j * g_cfg.n_ltf + n)] = (float)mxGetDoubles(prhs[2])[n * g_cfg.n_tx + j];
+        Pm[2 * (j * g_cfg.n_ltf + n) + 1] = 0.f;
+      }
+    fail(mamimo_set_pilots(g_engine, xp, Pm));
+  } else if (!strcmp(cmd, "load")) {
+    need_engine();
+    if (nrhs != 5 && nrhs != 9) mexErrMsgIdAndTxt("mamimo:usage", "load(net, layer, W, b [, gamma, beta, mean, var])");
+    for (int i = 3; i < nrhs; ++i)
+      if (!mxIsSingle(prhs[i])) mexErrMsgIdAndTxt("mamimo:type", "weights must be single");
+    const float* bn[4] = {NULL, NULL, NULL, NULL};
+    for (int i = 0; i < 4 && nrhs == 9; ++i) bn[i] = mxGetSingles(prhs[5 + i]);
+    fail(mamimo_load_layer(g_engine, (int)mxGetScalar(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetSingles(prhs[3]),
+                           mxGetSingles(prhs[4]), bn[0], bn[1], bn[2], bn[3]));
+  } else if (!strcmp(cmd, "finalize")) {
+    need_engine();
+    fail(mamimo_finalize_weights(g_engine));
+  } else if (!strcmp(cmd, "ls") || !strcmp(cmd, "estimate")) {
+    need_engine();
+    if (nrhs < 2) mexErrMsgIdAndTxt("mamimo:usage", "rxData missing");
+    const mwSize np = check_rx(prhs[1], &g_cfg);
+    const mwSize dims[4] = {(mwSize)g_cfg.n_sc, (mwSize)g_cfg.n_tx, (mwSize)g_cfg.n_rx, np};
+    plhs[0] = mxCreateNumericArray(np > 1 ? 4 : 3, dims, mxDOUBLE_CLASS, mxCOMPLEX);   // hD [Nsc x numSTS x Nr (x Npkt)]
+    fail(mamimo_ls_estimate(g_engine, mxGetComplexDoubles(prhs[1]), MAMIMO_C128, MAMIMO_MEM_HOST, (int64_t)np,
+                            mxGetComplexDoubles(plhs[0]), MAMIMO_C128, MAMIMO_MEM_HOST, NULL));
+    if (!strcmp(cmd, "estimate")) {
+      if (nlhs < 3) mexErrMsgIdAndTxt("mamimo:usage", "[hD, Hr, Hi] = mamimo_mex('estimate', rxData)");
+      const mwSize od[2] = {(mwSize)g_cfg.d_out, (mwSize)g_cfg.n_tx * g_cfg.n_rx * np};   // column = pair row
+      plhs[1] = mxCreateNumericArray(2, od, mxSINGLE_CLASS, mxREAL);
+      plhs[2] = mxCreateNumericArray(2, od, mxSINGLE_CLASS, mxREAL);
+      fail(mamimo_estimate(g_engine, mxGetComplexDoubles(prhs[1]), MAMIMO_C128, (int64_t)np, NULL,
+                           mxGetSingles(plhs[1]), mxGetSingles(plhs[2]), MAMIMO_MEM_HOST, NULL));
+    }
+  } else {
+    mexErrMsgIdAndTxt("mamimo:usage", "unknown command '%s'", cmd);
+  }
+}

@@ -92,7 +92,8 @@ typedef struct {
   int32_t act_scale_log2;   /* FP16X3 only: power-of-two operand scale (default 6) */
   int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (2) */
   int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default */
-  int32_t reserved[5];
+  int32_t fc_single_cta;    /* 1 = use the 1-CTA FC kernel instead of the CTA-pair (cta_group::2) kernel */
+  int32_t reserved[4];
 } mamimo_config;
 
 typedef struct {
