@@ -185,16 +185,29 @@ def run_ours(args):
     if world > 1:
         gathered = [torch.empty((world * rows, NSC), dtype=torch.float32, device=dev) for _ in range(2)]
 
-    eng = mm.Engine(NT, NR, NSC, hidden=HIDDEN, precision=args.precision, max_pkts=args.max_pkts, device=local_rank)
+    eng = mm.Engine(NT, NR, NSC, hidden=HIDDEN, precision=args.precision, max_pkts=args.max_pkts, device=local_rank,
+                    fc_sm_reserve=(args.sm_reserve if world > 1 else 0))
     eng.set_pilots(x, None)
     eng.load_weights(nets)
     stream = torch.cuda.current_stream(dev)
 
+    # N > 1: the batch is estimated in n_gather_chunks pieces; each piece's all-gather (NCCL, own stream) overlaps
+    # the next piece's compute.  Gathered layout is chunk-major, rank-minor (sharding.gathered_row_index).
+    n_chunks = args.gather_chunks if world > 1 else 1
+    bounds = [(c * npkt // n_chunks, (c + 1) * npkt // n_chunks) for c in range(n_chunks)]
+    rpp = NT * NR
+
     def step_device():
-        eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
-        if world > 1:       # the one collective of the path: all-gather of H-hat planes
-            dist.all_gather_into_tensor(gathered[0], Hr)
-            dist.all_gather_into_tensor(gathered[1], Hi)
+        works = []
+        for lo, hi in bounds:
+            eng.estimate_raw(Yd[lo:hi].data_ptr(), 0, hi - lo, 0, Hr[lo * rpp:hi * rpp].data_ptr(),
+                             Hi[lo * rpp:hi * rpp].data_ptr(), 1, stream.cuda_stream)
+            if world > 1:       # the one collective of the path: all-gather of H-hat planes
+                g0, g1 = lo * rpp * world, hi * rpp * world
+                works.append(dist.all_gather_into_tensor(gathered[0][g0:g1], Hr[lo * rpp:hi * rpp], async_op=True))
+                works.append(dist.all_gather_into_tensor(gathered[1][g0:g1], Hi[lo * rpp:hi * rpp], async_op=True))
+        for w in works:
+            w.wait()
 
     def barrier():
         if world > 1:
@@ -321,6 +334,8 @@ def main():
     ap.add_argument("--max-pkts", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pieces per step whose all-gather overlaps compute")
+    ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
     args = ap.parse_args()
     # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library
     import importlib.util

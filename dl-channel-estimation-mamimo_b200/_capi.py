@@ -28,7 +28,8 @@ class Config(C.Structure):
         ("len_ltf", C.c_int32), ("max_pkts", C.c_int32), ("act_scale_log2", C.c_int32),
         ("kb_per_chunk", C.c_int32), ("host_chunk_pkts", C.c_int32),
         ("fc_single_cta", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("fc_sm_reserve", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 

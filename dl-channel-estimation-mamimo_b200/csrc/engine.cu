@@ -63,10 +63,11 @@ struct mamimo_engine {
   mamimo_config cfg;
   std::string err;
   int num_sms = 0;
+  int fc_sms = 0;               // SMs the persistent FC kernels may occupy
   int rows_per_pkt = 0;
   int max_pkts = 0;
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
-  int kb_per_chunk = 2;
+  int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
@@ -260,7 +261,7 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
     if (e->fc_pair) {
       using Cfg2 = FcTc2Cfg<S>;
       const int pair_tiles = ((a.M + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((a.N + kTcBN - 1) / kTcBN);
-      const int grid2 = 2 * std::min(pair_tiles, e->num_sms / 2);
+      const int grid2 = 2 * std::min(pair_tiles, e->fc_sms / 2);
       const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
       fc_tc2_kernel<S><<<grid2, kFcThreads, smem2, st>>>(d.tmap_a, d.tmap_b_half, a);
       CK(e, cudaGetLastError());
@@ -269,7 +270,7 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
     }
     using Cfg = FcTcCfg<S, kTcBN>;
     const int tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcBN - 1) / kTcBN);
-    const int grid = std::min(tiles, e->num_sms);
+    const int grid = std::min(tiles, e->fc_sms);
     const int smem = Cfg::kStages * Cfg::kStageBytes + Cfg::kAuxBytes + 1024;
     fc_tc_kernel<S, kTcBN><<<grid, kFcThreads, smem, st>>>(d.tmap_a, d.tmap_b, a);
   }
@@ -571,6 +572,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   e->cfg = *cfg;
   memset(&e->stats, 0, sizeof(e->stats));
   e->num_sms = prop.multiProcessorCount;
+  e->fc_sms = std::max(2, e->num_sms - std::max(0, cfg->fc_sm_reserve));
   e->rows_per_pkt = cfg->n_tx * cfg->n_rx;
   e->n_pil = (cfg->n_sc + cfg->n_ps - 1) / cfg->n_ps;
   e->n_layers = has_mlp ? cfg->n_hidden + 1 : 0;
@@ -593,7 +595,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   // host pipeline granularity: ~8K rows per chunk so H2D, compute and D2H of neighbouring chunks overlap
   e->host_chunk = cfg->host_chunk_pkts > 0 ? std::min(cfg->host_chunk_pkts, e->max_pkts)
                                            : std::min(e->max_pkts, std::max(1, 8192 / rows_per_unit));
-  e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 2;
+  e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 4;
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;

@@ -59,7 +59,7 @@ class Engine:
 
     def __init__(self, n_tx, n_rx, n_sc, n_ltf=None, n_ps=1, hidden=(1024, 1024), d_in=None, d_out=None,
                  input_mode="ls", precision="tf32x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=6,
-                 mlp=True, kb_per_chunk=0, host_chunk_pkts=0, fc_single_cta=False):
+                 mlp=True, kb_per_chunk=0, host_chunk_pkts=0, fc_single_cta=False, fc_sm_reserve=0):
         cfg = _capi.Config()
         lib.mamimo_config_init(C.byref(cfg))
         cfg.device = device
@@ -83,6 +83,7 @@ class Engine:
         cfg.kb_per_chunk = kb_per_chunk
         cfg.host_chunk_pkts = host_chunk_pkts
         cfg.fc_single_cta = 1 if fc_single_cta else 0
+        cfg.fc_sm_reserve = fc_sm_reserve
         self.cfg = cfg
         self.precision = precision
         self.input_mode = input_mode

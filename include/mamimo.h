@@ -90,10 +90,11 @@ typedef struct {
   int32_t len_ltf;          /* mode A only: time-domain samples per (pkt,rx) fed to the net */
   int32_t max_pkts;         /* packets per internal chunk (workspace sizing); 0 = default */
   int32_t act_scale_log2;   /* FP16X3 only: power-of-two operand scale (default 6) */
-  int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (2) */
+  int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (4) */
   int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default */
   int32_t fc_single_cta;    /* 1 = use the 1-CTA FC kernel instead of the CTA-pair (cta_group::2) kernel */
-  int32_t reserved[4];
+  int32_t fc_sm_reserve;    /* SMs the persistent FC kernels leave free (room for a concurrent NCCL all-gather) */
+  int32_t reserved[3];
 } mamimo_config;
 
 typedef struct {

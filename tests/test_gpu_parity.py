@@ -277,3 +277,83 @@ def test_mode_a_time_domain_plus_p_row(golden_dir):
     Xi = np.concatenate([z["Xsig_imag"], z["Xp_imag"]], axis=1)
     assert rel_l2(mlp.forward(Xr, nets["real"]), Yr) <= TOL_DNN
     assert rel_l2(mlp.forward(Xi, nets["imag"]), Yi) <= TOL_DNN
+
+
+# ------------------------------------------------------------------------------ larger configs / variants
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3"])
+def test_full_path_config4_shape(precision):
+    """BASELINE config-4 shape: Nt64 Nr8, 2048 sc, FC 2048-1024-1024-2048, one packet = 512 pair rows."""
+    nt, nr, nsc, npkt = 64, 8, 2048, 1
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, (1024, 1024), nsc)
+    Y, _ = mm.synth.make_packets(4, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    with mm.Engine(nt, nr, nsc, hidden=(1024, 1024), precision=precision, max_pkts=2) as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr, Hi, Hls = eng.estimate(Y, want_ls=True)
+    ref_ls, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
+    assert rel_l2(ref_ls, Hls) <= TOL_LS
+    assert rel_l2(ref_r + 1j * ref_i, Hr.astype(np.float64) + 1j * Hi) <= TOL_DNN
+
+
+@pytest.mark.parametrize("single_cta", [False, True])
+@pytest.mark.parametrize("kbc", [1, 4, 1000])
+def test_fc_kernel_variants_agree_with_oracle(single_cta, kbc):
+    """CTA-pair vs 1-CTA kernel, and accumulation-chain lengths: chain 1000 = whole K in the tensor core
+    (the truncating-accumulate regime) must still be < 1e-5 for fp16x3 at K=1024 but is visibly worse."""
+    rows, d = 700, 1024
+    nets = mm.synth.make_nets(d, (d, d), d)
+    rng = np.random.default_rng(9)
+    Xr = rng.standard_normal((rows, d)).astype(np.float32)
+    Xi = rng.standard_normal((rows, d)).astype(np.float32)
+    with mm.Engine(1, 1, 1, n_ltf=1, hidden=(d, d), d_in=d, d_out=d, input_mode="planes", precision="fp16x3",
+                   kb_per_chunk=kbc, fc_single_cta=single_cta) as eng:
+        eng.load_weights(nets)
+        Yr, Yi = eng.predict_planes(Xr, Xi)
+    err = max(rel_l2(mlp.forward(Xr, nets["real"]), Yr), rel_l2(mlp.forward(Xi, nets["imag"]), Yi))
+    assert err <= (1.2e-5 if kbc == 1000 else 4e-6), err
+
+
+def test_full_batch_properties_config2():
+    """BASELINE config-2 size (500 packets, device-resident): per-packet independence -- packet p of the batch
+    result is bitwise the single-packet result -- and a sampled packet agrees with the oracle."""
+    import torch
+    nt, nr, nsc, npkt = 32, 4, 1024, 500
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, (1024, 1024), nsc)
+    Yg, _ = mm.synth.make_packets(1, 20, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    Y = np.concatenate([Yg] * 25)
+    rows = nt * nr
+    with mm.Engine(nt, nr, nsc, hidden=(1024, 1024), precision="fp16x3") as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr, Hi = eng.estimate(torch.from_numpy(Y).cuda())
+        torch.cuda.synchronize()
+        Hr, Hi = Hr.cpu().numpy(), Hi.cpu().numpy()
+        for p in (0, 137, 499):
+            r1, i1 = eng.estimate(Y[p:p + 1])
+            assert np.array_equal(r1, Hr[p * rows:(p + 1) * rows]) and np.array_equal(i1, Hi[p * rows:(p + 1) * rows])
+    # tiled input => tiled output (idempotence over the batch axis)
+    assert np.array_equal(Hr[:20 * rows], Hr[20 * rows:40 * rows])
+    _, ref_r, ref_i = oracle_full(Y[137:138], tables.sylvester_hadamard(nt), x, 1, nets)
+    got = Hr[137 * rows:138 * rows].astype(np.float64) + 1j * Hi[137 * rows:138 * rows]
+    assert rel_l2(ref_r + 1j * ref_i, got) <= TOL_DNN
+
+
+def test_test_mode_driver_writes_reference_file_contract(tmp_path):
+    """run_test_mode -> test_csi_predictions_{real,imag}_<pkt>.mat -> the reader BER_test_maMIMO_LTF.m implements."""
+    nt, nr, nsc, npkt = 8, 2, 64, 3
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, (64,), nsc)
+    Y, _ = mm.synth.make_packets(6, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    with mm.Engine(nt, nr, nsc, hidden=(64,), precision="tf32x3") as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr, Hi, Hls = mm.pipeline.run_test_mode(eng, Y, str(tmp_path))
+    _, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
+    for p in range(npkt):
+        csi, x_r, x_i = mm.pipeline.read_prediction_files(str(tmp_path), p + 1, nt, nr)
+        sl = slice(p * nt * nr, (p + 1) * nt * nr)
+        want = postproc.rows_to_csi(ref_r[sl] + 1j * ref_i[sl], nt, nr)
+        assert rel_l2(want, csi) <= TOL_DNN
+        assert np.array_equal(x_r, Hls[p].reshape(-1, nsc).real)
