@@ -191,23 +191,20 @@ def run_ours(args):
     eng.load_weights(nets)
     stream = torch.cuda.current_stream(dev)
 
-    # N > 1: the batch is estimated in n_gather_chunks pieces; each piece's all-gather (NCCL, own stream) overlaps
-    # the next piece's compute.  Gathered layout is chunk-major, rank-minor (sharding.gathered_row_index).
-    n_chunks = args.gather_chunks if world > 1 else 1
-    bounds = [(c * npkt // n_chunks, (c + 1) * npkt // n_chunks) for c in range(n_chunks)]
-    rpp = NT * NR
-
+    # N > 1: the one collective of the path is the all-gather of the H-hat planes.  The real plane is final after
+    # the real net, so its gather (NCCL, own stream) overlaps the imaginary net's three layers; the FC kernels
+    # leave --sm-reserve SMs free so the NCCL kernel never blocks a persistent CTA.
     def step_device():
-        works = []
-        for lo, hi in bounds:
-            eng.estimate_raw(Yd[lo:hi].data_ptr(), 0, hi - lo, 0, Hr[lo * rpp:hi * rpp].data_ptr(),
-                             Hi[lo * rpp:hi * rpp].data_ptr(), 1, stream.cuda_stream)
-            if world > 1:       # the one collective of the path: all-gather of H-hat planes
-                g0, g1 = lo * rpp * world, hi * rpp * world
-                works.append(dist.all_gather_into_tensor(gathered[0][g0:g1], Hr[lo * rpp:hi * rpp], async_op=True))
-                works.append(dist.all_gather_into_tensor(gathered[1][g0:g1], Hi[lo * rpp:hi * rpp], async_op=True))
-        for w in works:
-            w.wait()
+        if world == 1:
+            eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+            return
+        eng.estimate_stages_raw(eng.STAGE_LS | eng.STAGE_NET_REAL, Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), 0,
+                                stream.cuda_stream)
+        w0 = dist.all_gather_into_tensor(gathered[0], Hr, async_op=True)
+        eng.estimate_stages_raw(eng.STAGE_NET_IMAG, 0, 0, npkt, 0, 0, Hi.data_ptr(), stream.cuda_stream)
+        w1 = dist.all_gather_into_tensor(gathered[1], Hi, async_op=True)
+        w0.wait()
+        w1.wait()
 
     def barrier():
         if world > 1:
@@ -334,7 +331,6 @@ def main():
     ap.add_argument("--max-pkts", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pieces per step whose all-gather overlaps compute")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
     args = ap.parse_args()
     # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library

@@ -281,8 +281,10 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
 
 // all FC layers of both nets for n_rows rows already staged in act_in[0/1]
 template <int S>
-mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, cudaStream_t st) {
+mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, cudaStream_t st,
+                      unsigned net_mask = 3u) {
   for (int net = 0; net < 2; ++net) {
+    if (!(net_mask & (1u << net))) continue;
     for (int l = 0; l < e->n_layers; ++l) {
       const DevLayer& d = e->dl[net][l];
       const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
@@ -789,13 +791,19 @@ mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y
                      static_cast<cudaStream_t>(stream), stage);
 }
 
-mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type, int64_t n_pkt, void* H_ls,
-                              float* H_real, float* H_imag, mamimo_mem mem, void* stream) {
+mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_ctype y_type, int64_t n_pkt, void* H_ls,
+                                     float* H_real, float* H_imag, mamimo_mem mem, void* stream, uint32_t stages) {
   if (!e) return MAMIMO_ERR_INVALID;
   if (e->cfg.input_mode != MAMIMO_INPUT_LS) return fail(e, MAMIMO_ERR_STATE, "engine not configured for mode C (INPUT_LS)");
   if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
   if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
-  if (n_pkt < 0 || (n_pkt > 0 && (!Y || !H_real || !H_imag))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  const uint32_t all = MAMIMO_STAGE_LS | MAMIMO_STAGE_NET_REAL | MAMIMO_STAGE_NET_IMAG;
+  if (stages == 0 || (stages & ~all)) return fail(e, MAMIMO_ERR_INVALID, "bad stage mask");
+  if (stages != all && (mem != MAMIMO_MEM_DEVICE || n_pkt > e->max_pkts))
+    return fail(e, MAMIMO_ERR_INVALID, "partial stage masks need device buffers and n_pkt <= max_pkts (one chunk)");
+  if (n_pkt < 0 || (n_pkt > 0 && (((stages & MAMIMO_STAGE_LS) && !Y) || ((stages & MAMIMO_STAGE_NET_REAL) && !H_real) ||
+                                  ((stages & MAMIMO_STAGE_NET_IMAG) && !H_imag))))
+    return fail(e, MAMIMO_ERR_INVALID, "null buffer");
   if ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(H_ls) | reinterpret_cast<uintptr_t>(H_real) |
        reinterpret_cast<uintptr_t>(H_imag)) & 15)
     return fail(e, MAMIMO_ERR_INVALID, "Y, H_ls, H_real and H_imag must be 16-byte aligned");
@@ -804,12 +812,23 @@ mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_ty
   const size_t hlsb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.n_sc * 8;
   const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
-    mamimo_status s = DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, 0, true, st)));
+    mamimo_status s = MAMIMO_OK;
+    if (stages & MAMIMO_STAGE_LS)
+      s = DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, 0, true, st)));
     if (s != MAMIMO_OK) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+    const unsigned nets = (stages >> 1) & 3u;
+    if (!nets) return s;
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st, nets)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type, int64_t n_pkt, void* H_ls,
+                              float* H_real, float* H_imag, mamimo_mem mem, void* stream) {
+  if (n_pkt > 0 && (!Y || !H_real || !H_imag)) return e ? fail(e, MAMIMO_ERR_INVALID, "null buffer") : MAMIMO_ERR_INVALID;
+  return mamimo_estimate_stages(e, Y, y_type, n_pkt, H_ls, H_real, H_imag, mem, stream,
+                                MAMIMO_STAGE_LS | MAMIMO_STAGE_NET_REAL | MAMIMO_STAGE_NET_IMAG);
 }
 
 mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const float* X_imag, int64_t n_rows,

@@ -141,6 +141,15 @@ class Engine:
                                   C.c_void_p(hr_ptr), C.c_void_p(hi_ptr), mem, C.c_void_p(stream) if stream else None),
               self._h)
 
+    STAGE_LS, STAGE_NET_REAL, STAGE_NET_IMAG = 1, 2, 4
+
+    def estimate_stages_raw(self, stages, y_ptr, y_type, n_pkt, hls_ptr, hr_ptr, hi_ptr, stream=0):
+        """Piecewise run on device buffers (mamimo_estimate_stages): lets the caller overlap e.g. the all-gather
+        of the real plane with the imaginary net."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        check(lib.mamimo_estimate_stages(self._h, vp(y_ptr), y_type, n_pkt, vp(hls_ptr), vp(hr_ptr), vp(hi_ptr),
+                                         _capi.MEM_DEVICE, vp(stream), stages), self._h)
+
     def ls_estimate_raw(self, y_ptr, y_type, n_pkt, h_ptr, h_type, mem, stream=0):
         check(lib.mamimo_ls_estimate(self._h, C.c_void_p(y_ptr), y_type, mem, n_pkt, C.c_void_p(h_ptr), h_type, mem,
                                      C.c_void_p(stream) if stream else None), self._h)

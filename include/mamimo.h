@@ -162,6 +162,16 @@ MAMIMO_API mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo
                                          int64_t n_pkt, void* H_ls, float* H_real, float* H_imag,
                                          mamimo_mem mem, void* stream);
 
+/* The same path run piecewise so a caller can overlap its own work (e.g. the all-gather of the real plane)
+ * with the remaining stages.  stages is a mask of MAMIMO_STAGE_*; LS leaves the operand planes of both
+ * nets in the engine's workspace, the NET stages consume them.  Partial masks: device buffers, one chunk. */
+#define MAMIMO_STAGE_LS 1u
+#define MAMIMO_STAGE_NET_REAL 2u
+#define MAMIMO_STAGE_NET_IMAG 4u
+MAMIMO_API mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_ctype y_type,
+                                                int64_t n_pkt, void* H_ls, float* H_real, float* H_imag,
+                                                mamimo_mem mem, void* stream, uint32_t stages);
+
 /* Mode B: rows of caller-supplied planes (float32 [n_rows][d_in]) -> (float32 [n_rows][d_out]) x2.
  * This is what CSIPredictor.inference does with X.real / X.imag (inference.py:29-30). */
 MAMIMO_API mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const float* X_imag,
