@@ -40,7 +40,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None

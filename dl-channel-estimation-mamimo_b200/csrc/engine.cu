@@ -597,6 +597,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   // host pipeline granularity: ~8K rows per chunk so H2D, compute and D2H of neighbouring chunks overlap
   e->host_chunk = cfg->host_chunk_pkts > 0 ? std::min(cfg->host_chunk_pkts, e->max_pkts)
                                            : std::min(e->max_pkts, std::max(1, 8192 / rows_per_unit));
+  if (const char* env = getenv("MAMIMO_HOST_CHUNK")) { if (atoi(env) > 0) e->host_chunk = std::min(atoi(env), e->max_pkts); }
   e->kb_per_chunk = cfg->kb_per_chunk > 0 ? cfg->kb_per_chunk : 4;
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   e->fc_pair = cfg->fc_single_cta == 0;
