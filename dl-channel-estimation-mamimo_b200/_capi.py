@@ -51,6 +51,7 @@ SYMBOLS = [
     "mamimo_ls_estimate", "mamimo_estimate", "mamimo_estimate_stages", "mamimo_predict_planes", "mamimo_predict_time",
     "mamimo_synchronize", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end",
+    "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time",
 ]
 
 
@@ -85,6 +86,9 @@ def _load():
         "mamimo_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "mamimo_host_alloc": (vp, [C.c_size_t]),
         "mamimo_host_free": (None, [vp]),
+        "mamimo_set_ofdm": (i32, [vp, i32, i32, i32, C.POINTER(i32)]),
+        "mamimo_ofdm_demod": (i32, [vp, vp, i32, i64, vp, i32, vp]),
+        "mamimo_estimate_time": (i32, [vp, vp, i32, i64, vp, vp, vp, i32, vp]),
         "mamimo_profile_begin": (i32, [vp]),
         "mamimo_profile_end": (i32, [vp, C.POINTER(Profile)]),
     }

@@ -15,6 +15,7 @@
 #include "../../include/mamimo.h"
 #include "fc.cuh"
 #include "ls.cuh"
+#include "ofdm.cuh"
 #include "tables.h"
 
 using namespace mm;
@@ -83,6 +84,11 @@ struct mamimo_engine {
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
   Operand act_h[2];             // ping-pong hidden activations (shared by both nets)
+  // OFDM front-end (optional)
+  int fft_len = 0, cp_len = 0, sym_offset = 0;
+  float2* d_twiddle = nullptr;
+  int* d_bins = nullptr;
+  float2* d_ydemod = nullptr;   // [max_pkts][n_rx][n_ltf][n_sc] scratch between demod and LS
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;  // pinned
   // host-memory pipeline
@@ -119,7 +125,7 @@ mamimo_status fail_cuda(mamimo_engine* e, cudaError_t ce, const char* what) {
     if (ce_ != cudaSuccess) return fail_cuda(e, ce_, #call); \
   } while (0)
 
-enum { kClsLs = 0, kClsFc = 1, kClsStage = 2 };
+enum { kClsLs = 0, kClsFc = 1, kClsStage = 2 };   // the OFDM demod kernel is booked under kClsStage
 // RAII event bracket around one launch (no-op unless profiling)
 struct ProfScope {
   mamimo_engine* e; cudaStream_t st; int idx = -1;
@@ -360,6 +366,29 @@ mamimo_status run_stage_time(mamimo_engine* e, const float* dSr, const float* dS
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
   }
+  return MAMIMO_OK;
+}
+
+mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n_pkt, float2* dY, cudaStream_t st) {
+  OfdmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = dx; a.Y = dY; a.twiddle = e->d_twiddle; a.bins = e->d_bins;
+  a.fft_len = e->fft_len; a.cp_len = e->cp_len; a.sym_offset = e->sym_offset;
+  a.n_sym = e->cfg.n_ltf; a.n_sc = e->cfg.n_sc; a.x_double = x_double;
+  int lg = 0;
+  while ((1 << lg) < e->fft_len) ++lg;
+  a.log2_fft = lg;
+  const long long grid = n_pkt * e->cfg.n_rx * e->cfg.n_ltf;
+  const int threads = std::min(256, std::max(32, e->fft_len / 2));
+  const size_t smem = static_cast<size_t>(2) * e->fft_len * sizeof(float2);
+  if (smem > 48 * 1024)
+    CK(e, cudaFuncSetAttribute(ofdm_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  {
+    ProfScope ps(e, st, kClsStage);
+    ofdm_demod_kernel<<<static_cast<unsigned>(grid), threads, smem, st>>>(a);
+  }
+  CK(e, cudaGetLastError());
+  e->stats.kernel_launches++;
   return MAMIMO_OK;
 }
 
@@ -654,7 +683,7 @@ void mamimo_destroy(mamimo_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags);
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -866,6 +895,81 @@ mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const
   };
   return run_chunked(e, n_pkt, e->max_pkts, sig_real, xb, sig_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len, int32_t sym_offset,
+                              const int32_t* carriers) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (fft_len < 2 || fft_len > 4096 || (fft_len & (fft_len - 1))) return fail(e, MAMIMO_ERR_INVALID, "fft_len must be a power of two in [2, 4096]");
+  if (cp_len < 0 || sym_offset < 0 || sym_offset > cp_len) return fail(e, MAMIMO_ERR_INVALID, "need 0 <= sym_offset <= cp_len");
+  if (!carriers) return fail(e, MAMIMO_ERR_INVALID, "carriers is NULL");
+  if (e->cfg.n_sc > fft_len) return fail(e, MAMIMO_ERR_INVALID, "n_sc exceeds fft_len");
+  CK(e, cudaSetDevice(e->cfg.device));
+  std::vector<int> bins(e->cfg.n_sc);
+  for (int k = 0; k < e->cfg.n_sc; ++k) {
+    if (carriers[k] < 1 || carriers[k] > fft_len) return fail(e, MAMIMO_ERR_INVALID, "carrier index out of range");
+    bins[k] = (carriers[k] - 1 + fft_len / 2) % fft_len;      // undo fftshift: shifted index -> natural FFT bin
+  }
+  std::vector<float> tw(static_cast<size_t>(fft_len));        // [fft/2] complex
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < fft_len / 2; ++k) {
+    tw[2 * k] = static_cast<float>(std::cos(two_pi * k / fft_len));
+    tw[2 * k + 1] = static_cast<float>(-std::sin(two_pi * k / fft_len));
+  }
+  if (e->d_twiddle) { cudaFree(e->d_twiddle); e->d_twiddle = nullptr; }
+  if (e->d_bins) { cudaFree(e->d_bins); e->d_bins = nullptr; }
+  CK(e, cudaMalloc(&e->d_twiddle, std::max<size_t>(8, tw.size() * sizeof(float))));
+  CK(e, cudaMalloc(&e->d_bins, bins.size() * sizeof(int)));
+  CK(e, cudaMemcpy(e->d_twiddle, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(e, cudaMemcpy(e->d_bins, bins.data(), bins.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!e->d_ydemod)
+    CK(e, cudaMalloc(&e->d_ydemod, static_cast<size_t>(e->max_pkts) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * sizeof(float2)));
+  e->fft_len = fft_len; e->cp_len = cp_len; e->sym_offset = sym_offset;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_ofdm_demod(mamimo_engine* e, const void* x, mamimo_ctype x_type, int64_t n_pkt, void* Y,
+                                mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (!e->fft_len) return fail(e, MAMIMO_ERR_STATE, "OFDM front-end not configured (mamimo_set_ofdm)");
+  if (n_pkt < 0 || (n_pkt > 0 && (!x || !Y))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Y)) & 15) return fail(e, MAMIMO_ERR_INVALID, "x and Y must be 16-byte aligned");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t xb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * (e->fft_len + e->cp_len) * (x_type == MAMIMO_C128 ? 16 : 8);
+  const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * 8;
+  auto stage = [&](int64_t n, const void* in0, const void*, void* out, float*, float*, cudaStream_t st) {
+    return run_ofdm(e, in0, x_type == MAMIMO_C128, n, static_cast<float2*>(out), st);
+  };
+  return run_chunked(e, n_pkt, e->max_pkts, x, xb, nullptr, 0, Y, yb, nullptr, nullptr, 0, mem,
+                     static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype x_type, int64_t n_pkt, void* H_ls,
+                                   float* H_real, float* H_imag, mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (!e->fft_len) return fail(e, MAMIMO_ERR_STATE, "OFDM front-end not configured (mamimo_set_ofdm)");
+  if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
+  const bool mlp = e->n_layers > 0;
+  if (mlp && e->cfg.input_mode != MAMIMO_INPUT_LS) return fail(e, MAMIMO_ERR_STATE, "engine not configured for mode C (INPUT_LS)");
+  if (mlp && !e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
+  if (n_pkt < 0 || (n_pkt > 0 && (!x || (mlp && (!H_real || !H_imag)) || (!mlp && !H_ls))))
+    return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(H_ls) | reinterpret_cast<uintptr_t>(H_real) |
+       reinterpret_cast<uintptr_t>(H_imag)) & 15)
+    return fail(e, MAMIMO_ERR_INVALID, "buffers must be 16-byte aligned");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t xb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * (e->fft_len + e->cp_len) * (x_type == MAMIMO_C128 ? 16 : 8);
+  const size_t hlsb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.n_sc * 8;
+  const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
+  auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
+    mamimo_status s = run_ofdm(e, in0, x_type == MAMIMO_C128, n, e->d_ydemod, st);
+    if (s != MAMIMO_OK) return s;
+    s = DISPATCH_S(e, (run_ls<S>(e, e->d_ydemod, 0, static_cast<int>(n), hls, 0, mlp, st)));
+    if (s != MAMIMO_OK || !mlp) return s;
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+  };
+  return run_chunked(e, n_pkt, e->max_pkts, x, xb, nullptr, 0, H_ls, hlsb, mlp ? H_real : nullptr,
+                     mlp ? H_imag : nullptr, hb, mem, static_cast<cudaStream_t>(stream), stage);
 }
 
 mamimo_status mamimo_synchronize(mamimo_engine* e) {

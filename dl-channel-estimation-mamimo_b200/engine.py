@@ -248,6 +248,50 @@ class Engine:
                                       _capi.MEM_HOST, None), self._h)
         return Yr, Yi
 
+    # ------------------------------------------------------------------ OFDM front-end
+    def set_ofdm(self, fft_len, cp_len, sym_offset, carriers_1based):
+        """ofdmdemod parameters (pg/generate_maMIMO_LTF.m:336-338); carriers = prm.CarriersLocations (1-based)."""
+        car = np.ascontiguousarray(np.asarray(carriers_1based, dtype=np.int32).ravel())
+        if car.size != self.cfg.n_sc:
+            raise ValueError("need n_sc=%d carrier indices" % self.cfg.n_sc)
+        check(lib.mamimo_set_ofdm(self._h, fft_len, cp_len, sym_offset, car.ctypes.data_as(C.POINTER(C.c_int32))), self._h)
+        self._sym_len = fft_len + cp_len
+
+    def _x_info(self, x):
+        c = self.cfg
+        want = (c.n_rx, c.n_ltf * self._sym_len)
+        if x.ndim != 3 or tuple(x.shape[1:]) != want:
+            raise ValueError("x must be [n_pkt, n_rx=%d, n_ltf*(fft+cp)=%d]" % want)
+        if x.dtype not in (np.complex64, np.complex128):
+            raise TypeError("x must be complex64 or complex128")
+        return int(x.shape[0]), (_capi.C128 if x.dtype == np.complex128 else _capi.C64)
+
+    def ofdm_demod(self, x):
+        """time-domain x [n_pkt, n_rx, n_ltf*(fft+cp)] -> Y complex64 [n_pkt, n_rx, n_ltf, n_sc] (host arrays)."""
+        x = np.ascontiguousarray(x)
+        n_pkt, t = self._x_info(x)
+        c = self.cfg
+        Y = np.empty((n_pkt, c.n_rx, c.n_ltf, c.n_sc), dtype=np.complex64)
+        check(lib.mamimo_ofdm_demod(self._h, _np_ptr(x), t, n_pkt, _np_ptr(Y), _capi.MEM_HOST, None), self._h)
+        return Y
+
+    def estimate_time(self, x, want_ls=False):
+        """demod -> LS -> FC from time-domain samples.  Returns (H_real, H_imag[, H_ls]); on an engine built with
+        mlp=False returns H_ls only."""
+        x = np.ascontiguousarray(x)
+        n_pkt, t = self._x_info(x)
+        c = self.cfg
+        mlp = c.d_out > 0
+        Hls = np.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=np.complex64) if (want_ls or not mlp) else None
+        Hr = np.empty((n_pkt * self.rows_per_pkt, c.d_out), dtype=np.float32) if mlp else None
+        Hi = np.empty_like(Hr) if mlp else None
+        check(lib.mamimo_estimate_time(self._h, _np_ptr(x), t, n_pkt, None if Hls is None else _np_ptr(Hls),
+                                       None if Hr is None else _np_ptr(Hr), None if Hi is None else _np_ptr(Hi),
+                                       _capi.MEM_HOST, None), self._h)
+        if not mlp:
+            return Hls
+        return (Hr, Hi, Hls) if want_ls else (Hr, Hi)
+
     def synchronize(self):
         check(lib.mamimo_synchronize(self._h), self._h)
 

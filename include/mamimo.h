@@ -184,6 +184,22 @@ MAMIMO_API mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_
                                              int64_t n_pkt, float* Y_real, float* Y_imag,
                                              mamimo_mem mem, void* stream);
 
+/* ---- next row: OFDM demodulation front-end ------------------
+ * Configure: FFT length (power of two, <= 4096), cyclic prefix, symbol sampling offset (0..cp_len; the
+ * reference passes cp_len) and the kept carriers (1-based indices into the fftshifted spectrum, i.e.
+ * prm.CarriersLocations, n_sc of them).  Replaces the ofdmdemod call at pg/generate_maMIMO_LTF.m:336-338. */
+MAMIMO_API mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len, int32_t sym_offset,
+                                         const int32_t* carriers_1based);
+/* x: time-domain samples, complex [n_pkt][n_rx][n_ltf*(fft_len+cp_len)] (MATLAB inputRXSig [lenLTF x Nr] per
+ * packet) -> Y complex64 [n_pkt][n_rx][n_ltf][n_sc], the layout mamimo_ls_estimate / mamimo_estimate take. */
+MAMIMO_API mamimo_status mamimo_ofdm_demod(mamimo_engine* e, const void* x, mamimo_ctype x_type, int64_t n_pkt,
+                                           void* Y, mamimo_mem mem, void* stream);
+/* Full path from the time domain: demod -> LS (+interp) -> both FC nets (H_real/H_imag may be NULL on an
+ * engine without an MLP; H_ls complex64 may be NULL). */
+MAMIMO_API mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype x_type, int64_t n_pkt,
+                                              void* H_ls, float* H_real, float* H_imag, mamimo_mem mem,
+                                              void* stream);
+
 MAMIMO_API mamimo_status mamimo_synchronize(mamimo_engine* e);
 MAMIMO_API mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out);
 /* begin: bracket every engine kernel with a CUDA event pair on its stream; end: synchronise and sum them */

@@ -174,7 +174,51 @@ def run_data_generator():
     return out
 
 
+# ---------------------------------------------------------------- 4. DataGenerator method='reshape' (OFDM demod mirror)
+def run_data_generator_reshape():
+    """massiveMIMO_dataGenerator.py:425-458 executed unmodified: the author's numpy mirror of ofdmdemod
+    (F-order reshape, CP removal with symOffset, FFT, fftshift).  Pins the oracle's OFDM front-end."""
+    sys.path.insert(0, REF)
+    import massiveMIMO_dataGenerator as ref_dg
+    out = {}
+    for tag, (fft_len, cp_len, sym_off, n_sym) in {"a": (16, 4, 4, 4), "b": (32, 8, 3, 2), "c": (64, 16, 16, 1)}.items():
+        n_tx, n_rx, n_pkt, nsc = n_sym, 2, 2, 5
+        rng = np.random.default_rng([67, fft_len])
+        len_ltf = (fft_len + cp_len) * n_sym
+        ltf = rng.standard_normal((n_pkt, n_rx, len_ltf)) + 1j * rng.standard_normal((n_pkt, n_rx, len_ltf))
+        P = rng.choice([-1.0, 1.0], size=(n_tx, n_tx))
+        ltf_freq = rng.choice([-1.0, 1.0], size=nsc)
+        X = np.zeros((n_pkt * n_rx * n_tx, 2), dtype=np.int64)
+        LTF = {}
+        for p in range(n_pkt):
+            for irx in range(n_rx):
+                h = 5000 + p * n_rx + irx
+                LTF[h] = {"real": ltf[p, irx].real.copy(), "imag": ltf[p, irx].imag.copy()}
+                for itx in range(n_tx):
+                    X[p * (n_rx * n_tx) + irx * n_tx + itx] = [h, itx]
+        y = np.zeros((X.shape[0], nsc))
+        dataset = {"X": X, "LTF": LTF, "P": P, "y": {"real": y, "imag": y}}
+        prm = {"lenLTF": len_ltf, "nTX": n_tx, "nRX": n_rx, "nSubCarr": nsc, "FFTLength": fft_len, "CPLen": cp_len,
+               "numSym": n_sym, "symOffset": sym_off, "ltf_freqdom": ltf_freq}
+        res = {}
+        for d in ("real", "imag"):
+            gen = ref_dg.DataGenerator(list(range(X.shape[0])), dataset, d, prm, datasource="matlab_maMimo",
+                                       method="reshape", batch_size=n_tx * n_rx)
+            gen.reorder_indexes()
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")            # the reference stores a complex FFT into a real array
+                res[d] = np.concatenate([gen[b][0] for b in range(len(gen))])
+        out["ltf_" + tag] = ltf
+        out["cfg_" + tag] = np.asarray([fft_len, cp_len, sym_off, n_sym, n_rx, n_pkt])
+        out["Xreal_" + tag] = res["real"]
+        out["Ximag_" + tag] = res["imag"]
+    return out
+
+
 def main():
+    install_stub_tf(lambda path: None)
+    np.savez_compressed(os.path.join(HERE, "ref_data_generator_reshape.npz"), **run_data_generator_reshape())
     np.savez_compressed(os.path.join(HERE, "ref_tables.npz"), **parse_tables())
     np.savez_compressed(os.path.join(HERE, "ref_inference_py.npz"), **run_inference_py())
     np.savez_compressed(os.path.join(HERE, "ref_data_generator.npz"), **run_data_generator())

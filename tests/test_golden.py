@@ -43,3 +43,30 @@ def test_mode_a_assembly_matches_reference_data_generator(golden_dir):
         assert np.array_equal(xsig, z["Xsig_" + d])
         assert np.array_equal(xp, z["Xp_" + d])
         assert np.array_equal(part(z["y"]), z["y_" + d])
+
+
+def test_ofdm_front_end_matches_reference_numpy_mirror(golden_dir):
+    """oracle.ofdm vs massiveMIMO_dataGenerator.py:425-458 (method='reshape') executed for real.
+    The mirror FFTs one real plane, keeps the real part, and its bare fftshift also rolls the symbol axis."""
+    from oracle import ofdm
+    z = np.load(os.path.join(golden_dir, "ref_data_generator_reshape.npz"))
+    for tag in "abc":
+        fft_len, cp, so, nsym, nrx, npkt = [int(v) for v in z["cfg_" + tag]]
+        ltf = z["ltf_" + tag]
+        for d, part in (("real", np.real), ("imag", np.imag)):
+            X = z["X%s_%s" % (d, tag)]
+            Y = ofdm.ofdm_demod(part(ltf), fft_len, cp, so, np.arange(1, fft_len + 1))
+            for row in range(X.shape[0]):
+                p, irx, itx = row // (nrx * nsym), (row // nsym) % nrx, row % nsym
+                sym = (itx - nsym // 2) % nsym
+                assert np.allclose(X[row, :fft_len], Y[p, irx, sym].real, rtol=0, atol=1e-12)
+
+
+def test_ofdm_mod_demod_round_trip():
+    from oracle import ofdm
+    rng = np.random.default_rng(3)
+    car = tables.carriers_locations()
+    G = rng.standard_normal((2, 3, 4, car.size)) + 1j * rng.standard_normal((2, 3, 4, car.size))
+    x = ofdm.ofdm_mod(G, 256, 64, car)
+    assert x.shape == (2, 3, 4 * 320)
+    assert np.max(np.abs(ofdm.ofdm_demod(x, 256, 64, 64, car) - G)) < 1e-12

@@ -380,3 +380,48 @@ def test_staged_estimate_matches_full_call():
         with pytest.raises(mm.MamimoError):        # partial masks are device-only
             import ctypes
             eng.estimate_stages_raw(0, Yd.data_ptr(), 0, npkt, 0, Hr2.data_ptr(), Hi2.data_ptr(), st)
+
+
+# ------------------------------------------------------------------------------ OFDM front-end
+@pytest.mark.parametrize("fft_len,cp,so,nt,nr,ctype", [(256, 64, 64, 32, 4, np.complex64), (256, 64, 64, 8, 2, np.complex128),
+                                                       (64, 16, 5, 4, 2, np.complex64), (1024, 256, 256, 4, 1, np.complex64),
+                                                       (2048, 512, 100, 2, 2, np.complex64)])
+def test_ofdm_demod_parity(fft_len, cp, so, nt, nr, ctype):
+    from oracle import ofdm
+    rng = np.random.default_rng(fft_len)
+    if fft_len == 256:
+        car = tables.carriers_locations()                     # reference numerology: 234 data carriers
+    else:
+        car = np.sort(rng.choice(np.arange(1, fft_len + 1), size=fft_len * 3 // 4, replace=False)).astype(np.int32)
+    npkt = 3
+    x = (rng.standard_normal((npkt, nr, nt * (fft_len + cp))) + 1j * rng.standard_normal((npkt, nr, nt * (fft_len + cp)))).astype(ctype)
+    with mm.Engine(nt, nr, car.size, mlp=False) as eng:
+        eng.set_ofdm(fft_len, cp, so, car)
+        Y = eng.ofdm_demod(x)
+    ref = ofdm.ofdm_demod(x, fft_len, cp, so, car)
+    assert Y.shape == ref.shape and Y.dtype == np.complex64
+    assert rel_l2(ref, Y) <= 2e-6                             # FP32 FFT vs FP64 oracle
+
+
+def test_estimate_from_time_domain_reference_numerology():
+    """Time-domain preamble -> ofdmdemod -> LS -> FC with the reference's 256/64/234 numerology, against
+    oracle demod + oracle LS + oracle FC; also equals the two-call path (demod, then estimate) bitwise."""
+    from oracle import ofdm
+    nt, nr, npkt = 8, 2, 3
+    car = tables.carriers_locations()
+    xp = tables.ltf_at_carriers().astype(np.float64)
+    nets = mm.synth.make_nets(234, (128,), 234)
+    Yf, _ = mm.synth.make_packets(31, npkt, nt, nr, 234, snr_db=10.0, x_tones=xp, dtype=np.complex128)
+    x = (ofdm.ofdm_mod(Yf, 256, 64, car) * 256).astype(np.complex64)       # some time-domain signal whose demod is ~Yf
+    with mm.Engine(nt, nr, 234, hidden=(128,), precision="tf32x3") as eng:
+        eng.set_pilots(xp, None)
+        eng.load_weights(nets)
+        eng.set_ofdm(256, 64, 64, car)
+        Hr, Hi, Hls = eng.estimate_time(x, want_ls=True)
+        Yd = eng.ofdm_demod(x)
+        Hr2, Hi2, Hls2 = eng.estimate(Yd, want_ls=True)
+    assert np.array_equal(Hr, Hr2) and np.array_equal(Hi, Hi2) and np.array_equal(Hls, Hls2)
+    Yref = ofdm.ofdm_demod(x, 256, 64, 64, car)
+    ref_ls, ref_r, ref_i = oracle_full(Yref, tables.sylvester_hadamard(nt), xp, 1, nets)
+    assert rel_l2(ref_ls, Hls) <= 3e-6
+    assert rel_l2(ref_r + 1j * ref_i, Hr.astype(np.float64) + 1j * Hi) <= TOL_DNN
