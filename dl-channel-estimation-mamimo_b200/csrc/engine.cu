@@ -375,12 +375,11 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
   a.x = dx; a.Y = dY; a.twiddle = e->d_twiddle; a.bins = e->d_bins;
   a.fft_len = e->fft_len; a.cp_len = e->cp_len; a.sym_offset = e->sym_offset;
   a.n_sym = e->cfg.n_ltf; a.n_sc = e->cfg.n_sc; a.x_double = x_double;
-  int lg = 0;
-  while ((1 << lg) < e->fft_len) ++lg;
-  a.log2_fft = lg;
-  const long long grid = n_pkt * e->cfg.n_rx * e->cfg.n_ltf;
-  const int threads = std::min(256, std::max(32, e->fft_len / 2));
-  const size_t smem = static_cast<size_t>(2) * e->fft_len * sizeof(float2);
+  a.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf;
+  a.syms_per_cta = std::max(1, std::min(16, 1024 / e->fft_len));   // >= one radix-4 butterfly per thread per stage
+  const long long grid = (a.total_syms + a.syms_per_cta - 1) / a.syms_per_cta;
+  const int threads = 256;
+  const size_t smem = static_cast<size_t>(a.syms_per_cta) * 2 * e->fft_len * sizeof(float2);
   if (smem > 48 * 1024)
     CK(e, cudaFuncSetAttribute(ofdm_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
@@ -910,9 +909,9 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
     if (carriers[k] < 1 || carriers[k] > fft_len) return fail(e, MAMIMO_ERR_INVALID, "carrier index out of range");
     bins[k] = (carriers[k] - 1 + fft_len / 2) % fft_len;      // undo fftshift: shifted index -> natural FFT bin
   }
-  std::vector<float> tw(static_cast<size_t>(fft_len));        // [fft/2] complex
+  std::vector<float> tw(static_cast<size_t>(2) * fft_len);    // [fft] complex: exp(-2 pi i m / fft)
   const double two_pi = 6.283185307179586476925286766559;
-  for (int k = 0; k < fft_len / 2; ++k) {
+  for (int k = 0; k < fft_len; ++k) {
     tw[2 * k] = static_cast<float>(std::cos(two_pi * k / fft_len));
     tw[2 * k + 1] = static_cast<float>(-std::sin(two_pi * k / fft_len));
   }

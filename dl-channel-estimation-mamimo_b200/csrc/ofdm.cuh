@@ -5,10 +5,11 @@
 //   massiveMIMO_dataGenerator.py:437-453 (F-order reshape into symbols, CP removal with symbol offset,
 //   FFT, fftshift along frequency, removal of null + pilot carriers).
 //
-// One CTA per (packet, rx, OFDM symbol): coalesced load of the FFT window (rotated so the true symbol
-// start comes first, dataGenerator.py:442), radix-2 Stockham autosort FFT in shared memory (ping-pong
-// buffers, twiddles from a host-computed FP64->FP32 table), then a gather of the data carriers written
-// straight into the LS stage's layout Y[pkt][rx][sym][k].  HBM-bound: (FFT+CP)*8 B in, Nsc*8 B out per symbol.
+// A CTA transforms `syms_per_cta` OFDM symbols of one (packet, rx) stream: coalesced load of each FFT window
+// (rotated so the true symbol start comes first, dataGenerator.py:442), radix-4 Stockham autosort FFT in
+// shared memory (ping-pong buffers, a trailing radix-2 stage when log2(FFT) is odd, twiddles from a
+// host-computed FP64->FP32 table), then a gather of the data carriers written straight into the LS stage's
+// layout Y[pkt][rx][sym][k].  HBM-bound: (FFT+CP)*8 B in, Nsc*8 B out per symbol.
 #pragma once
 #include "ptx.cuh"
 
@@ -17,54 +18,92 @@ namespace mm {
 struct OfdmArgs {
   const void* x;            // complex [n_pkt*n_rx][n_sym*(fft+cp)]  float2 or double2
   float2* Y;                // complex64 [n_pkt*n_rx][n_sym][n_sc]
-  const float2* twiddle;    // [fft/2]  exp(-2*pi*i*k/fft)
-  const int* bins;          // [n_sc]   natural-order FFT bin of each kept carrier
-  int fft_len, log2_fft, cp_len, sym_offset, n_sym, n_sc;
+  const float2* twiddle;    // [fft]  exp(-2*pi*i*m/fft)
+  const int* bins;          // [n_sc] natural-order FFT bin of each kept carrier
+  int fft_len, cp_len, sym_offset, n_sym, n_sc;
+  int syms_per_cta;         // symbols transformed side by side in one CTA
+  long long total_syms;     // n_pkt * n_rx * n_sym
   int x_double;
 };
 
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
 __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
-  extern __shared__ float2 sm_fft[];                 // [2][fft_len]
+  extern __shared__ float2 sm_fft[];                 // [syms_per_cta][2][fft_len]
   const int N = a.fft_len;
-  float2* buf0 = sm_fft;
-  float2* buf1 = sm_fft + N;
-  const int sym = blockIdx.x % a.n_sym;
-  const size_t prx = blockIdx.x / a.n_sym;
+  const int S = a.syms_per_cta;
+  const long long sym0 = static_cast<long long>(blockIdx.x) * S;
+  const int n_here = static_cast<int>(min(static_cast<long long>(S), a.total_syms - sym0));
   const int sym_len = N + a.cp_len;
-  const size_t base = (prx * a.n_sym + sym) * static_cast<size_t>(sym_len);
-  // window[i] = x[ix(i)],  ix = [cp, fft+off) ++ [off, cp)   (dataGenerator.py:442)
-  const int first = N + a.sym_offset - a.cp_len;     // length of the first run
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  // window[i] = x[ix(i)],  ix = [cp, fft+off) ++ [off, cp)   (dataGenerator.py:442).  Symbols of one (pkt,rx)
+  // stream are contiguous in x, and streams follow each other, so global symbol g starts at g * sym_len.
+  const int first = N + a.sym_offset - a.cp_len;
+  for (int idx = threadIdx.x; idx < n_here * N; idx += blockDim.x) {
+    const int s = idx / N, i = idx - s * N;
     const int src = (i < first) ? (a.cp_len + i) : (a.sym_offset + (i - first));
+    const size_t g = static_cast<size_t>(sym0 + s) * sym_len + src;
     float2 v;
     if (a.x_double) {
-      const double2 d = __ldg(reinterpret_cast<const double2*>(a.x) + base + src);
+      const double2 d = __ldg(reinterpret_cast<const double2*>(a.x) + g);
       v = make_float2(static_cast<float>(d.x), static_cast<float>(d.y));
     } else {
-      v = __ldg(reinterpret_cast<const float2*>(a.x) + base + src);
+      v = __ldg(reinterpret_cast<const float2*>(a.x) + g);
     }
-    buf0[i] = v;
+    sm_fft[static_cast<size_t>(s) * 2 * N + i] = v;
   }
   __syncthreads();
-  // Stockham radix-2: Ns = 1, 2, ..., N/2; output in natural order
-  const int half = N >> 1;
-  int tw_stride = half;                              // N / (2*Ns)
-  for (int ns = 1; ns < N; ns <<= 1, tw_stride >>= 1) {
-    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+
+  int cur = 0;                                        // which ping-pong half holds the data
+  const int quarter = N >> 2;
+  int ns = 1;
+  for (; ns * 4 <= N; ns <<= 2) {                     // radix-4 stages
+    const int stride = N / (4 * ns);
+    for (int idx = threadIdx.x; idx < n_here * quarter; idx += blockDim.x) {
+      const int s = idx / quarter, j = idx - s * quarter;
+      const float2* in = sm_fft + static_cast<size_t>(s) * 2 * N + cur * N;
+      float2* out = sm_fft + static_cast<size_t>(s) * 2 * N + (cur ^ 1) * N;
       const int k = j & (ns - 1);
-      const float2 w = a.twiddle[k * tw_stride];
-      const float2 u = buf0[j];
-      const float2 t = buf0[j + half];
-      const float2 v = make_float2(t.x * w.x - t.y * w.y, t.x * w.y + t.y * w.x);
-      const int d = ((j - k) << 1) + k;              // (j / ns) * 2ns + k
-      buf1[d] = make_float2(u.x + v.x, u.y + v.y);
-      buf1[d + ns] = make_float2(u.x - v.x, u.y - v.y);
+      const float2 v0 = in[j];
+      const float2 v1 = cmulf(in[j + quarter], a.twiddle[k * stride]);
+      const float2 v2 = cmulf(in[j + 2 * quarter], a.twiddle[2 * k * stride]);
+      const float2 v3 = cmulf(in[j + 3 * quarter], a.twiddle[3 * k * stride]);
+      const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+      const float2 t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+      const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+      const float2 t3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));      // (v1 - v3) * (-i)
+      const int d = ((j - k) << 2) + k;
+      out[d] = make_float2(t0.x + t2.x, t0.y + t2.y);
+      out[d + ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+      out[d + 2 * ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+      out[d + 3 * ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
     }
     __syncthreads();
-    float2* t = buf0; buf0 = buf1; buf1 = t;
+    cur ^= 1;
   }
-  float2* out = a.Y + (prx * a.n_sym + sym) * static_cast<size_t>(a.n_sc);
-  for (int k = threadIdx.x; k < a.n_sc; k += blockDim.x) out[k] = buf0[a.bins[k]];
+  if (ns < N) {                                       // one radix-2 stage left (log2 N odd)
+    const int half = N >> 1;
+    const int stride = N / (2 * ns);
+    for (int idx = threadIdx.x; idx < n_here * half; idx += blockDim.x) {
+      const int s = idx / half, j = idx - s * half;
+      const float2* in = sm_fft + static_cast<size_t>(s) * 2 * N + cur * N;
+      float2* out = sm_fft + static_cast<size_t>(s) * 2 * N + (cur ^ 1) * N;
+      const int k = j & (ns - 1);
+      const float2 u = in[j];
+      const float2 v = cmulf(in[j + half], a.twiddle[k * stride]);
+      const int d = ((j - k) << 1) + k;
+      out[d] = make_float2(u.x + v.x, u.y + v.y);
+      out[d + ns] = make_float2(u.x - v.x, u.y - v.y);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // symbols are contiguous in Y too ([stream][sym][k]): global symbol g writes at g * n_sc
+  for (int idx = threadIdx.x; idx < n_here * a.n_sc; idx += blockDim.x) {
+    const int s = idx / a.n_sc, k = idx - s * a.n_sc;
+    a.Y[static_cast<size_t>(sym0 + s) * a.n_sc + k] = sm_fft[static_cast<size_t>(s) * 2 * N + cur * N + a.bins[k]];
+  }
 }
 
 }  // namespace mm
