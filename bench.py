@@ -186,25 +186,37 @@ def run_ours(args):
         gathered = [torch.empty((world * rows, NSC), dtype=torch.float32, device=dev) for _ in range(2)]
 
     eng = mm.Engine(NT, NR, NSC, hidden=HIDDEN, precision=args.precision, max_pkts=args.max_pkts, device=local_rank,
-                    fc_sm_reserve=(args.sm_reserve if world > 1 else 0))
+                    fc_sm_reserve=(args.sm_reserve if (world > 1 and args.gather == "nccl") else 0))
     eng.set_pilots(x, None)
     eng.load_weights(nets)
     stream = torch.cuda.current_stream(dev)
 
-    # N > 1: the one collective of the path is the all-gather of the H-hat planes.  The real plane is final after
-    # the real net, so its gather (NCCL, own stream) overlaps the imaginary net's three layers; the FC kernels
-    # leave --sm-reserve SMs free so the NCCL kernel never blocks a persistent CTA.
+    # N > 1: the one collective of the path is the all-gather of the H-hat planes.
+    #  --gather fused (default): the final FC layer of each net TMA-stores every output tile straight into every
+    #      rank's gathered plane (peer memory over NVLink) -- compute and collective are one kernel; a 4-byte
+    #      all-reduce per step is the cross-rank completion signal a consumer would need.
+    #  --gather nccl: NCCL all-gather of each plane; the real plane's gather overlaps the imaginary net and the
+    #      FC kernels leave --sm-reserve SMs free so the NCCL kernel never blocks a persistent CTA.
+    fused = world > 1 and args.gather == "fused"
+    if fused:
+        g_real, g_imag = mm.sharding.connect_fused_gather(eng, npkt)
+        flag = torch.zeros(1, device=dev)
+    ALL = eng.STAGE_LS | eng.STAGE_NET_REAL | eng.STAGE_NET_IMAG
+
     def step_device():
         if world == 1:
             eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
-            return
-        eng.estimate_stages_raw(eng.STAGE_LS | eng.STAGE_NET_REAL, Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), 0,
-                                stream.cuda_stream)
-        w0 = dist.all_gather_into_tensor(gathered[0], Hr, async_op=True)
-        eng.estimate_stages_raw(eng.STAGE_NET_IMAG, 0, 0, npkt, 0, 0, Hi.data_ptr(), stream.cuda_stream)
-        w1 = dist.all_gather_into_tensor(gathered[1], Hi, async_op=True)
-        w0.wait()
-        w1.wait()
+        elif fused:
+            eng.estimate_stages_raw(ALL | eng.STAGE_GATHER, Yd.data_ptr(), 0, npkt, 0, 0, 0, stream.cuda_stream)
+            dist.all_reduce(flag)
+        else:
+            eng.estimate_stages_raw(eng.STAGE_LS | eng.STAGE_NET_REAL, Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), 0,
+                                    stream.cuda_stream)
+            w0 = dist.all_gather_into_tensor(gathered[0], Hr, async_op=True)
+            eng.estimate_stages_raw(eng.STAGE_NET_IMAG, 0, 0, npkt, 0, 0, Hi.data_ptr(), stream.cuda_stream)
+            w1 = dist.all_gather_into_tensor(gathered[1], Hi, async_op=True)
+            w0.wait()
+            w1.wait()
 
     def barrier():
         if world > 1:
@@ -249,6 +261,17 @@ def run_ours(args):
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         value_compute_only = world * npkt / (float(t.item()) / args.steps * 1e-3)
+
+    # fused gather self-check: the planes written by the kernels of all ranks == an NCCL all-gather of the same data
+    gather_check = None
+    if fused:
+        eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+        dist.all_gather_into_tensor(gathered[0], Hr)
+        dist.all_gather_into_tensor(gathered[1], Hi)
+        barrier()
+        ok = torch.tensor([int(torch.equal(gathered[0], g_real) and torch.equal(gathered[1], g_imag))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = bool(ok.item())
 
     # ---- timed region 2: end to end through the C ABI with pinned HOST buffers
     def step_host():
@@ -300,7 +323,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pkts_per_gpu": npkt, "precision": args.precision,
                        "l2": "inputs (0.5 GiB Y) and outputs (0.5 GiB) per step exceed the 126 MB L2",
-                       "parallelism": "packets sharded over %d GPU(s)%s" % (world, ", all-gather of H planes in step" if world > 1 else "")},
+                       "parallelism": "packets sharded over %d GPU(s)%s" % (
+                           world, (", all-gather of H planes in step (%s)" % args.gather) if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
                     "d2h_bytes_per_step": int(2 * rows * NSC * 4), "checksum": checksum},
@@ -310,6 +334,8 @@ def run_ours(args):
         }
         if value_compute_only is not None:
             line["value_compute_only"] = value_compute_only
+        if gather_check is not None:
+            line["fused_gather_equals_nccl"] = gather_check
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -331,6 +357,7 @@ def main():
     ap.add_argument("--max-pkts", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how H-hat is all-gathered")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
     args = ap.parse_args()
     # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library

@@ -52,6 +52,7 @@ SYMBOLS = [
     "mamimo_synchronize", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end",
     "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time",
+    "mamimo_gather_create", "mamimo_gather_connect", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
 ]
 
 
@@ -89,6 +90,11 @@ def _load():
         "mamimo_set_ofdm": (i32, [vp, i32, i32, i32, C.POINTER(i32)]),
         "mamimo_ofdm_demod": (i32, [vp, vp, i32, i64, vp, i32, vp]),
         "mamimo_estimate_time": (i32, [vp, vp, i32, i64, vp, vp, vp, i32, vp]),
+        "mamimo_gather_create": (i32, [vp, i32, i32, i64, C.POINTER(vp), C.POINTER(vp)]),
+        "mamimo_gather_connect": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "mamimo_ipc_export": (i32, [vp, C.c_char_p]),
+        "mamimo_ipc_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "mamimo_ipc_close": (i32, [vp]),
         "mamimo_profile_begin": (i32, [vp]),
         "mamimo_profile_end": (i32, [vp, C.POINTER(Profile)]),
     }

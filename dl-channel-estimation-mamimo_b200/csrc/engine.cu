@@ -84,6 +84,11 @@ struct mamimo_engine {
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
   Operand act_h[2];             // ping-pong hidden activations (shared by both nets)
+  // fused all-gather (optional): gathered planes [world * gather_rows][d_out] float32 per rank
+  int gather_world = 0, gather_rank = 0;
+  int64_t gather_rows = 0;                 // rows per rank slot
+  float* gather_local[2] = {nullptr, nullptr};                       // this rank's gathered planes (owned)
+  float* gather_peer[2][kMaxGatherRanks] = {};                       // every rank's planes as mapped here
   // OFDM front-end (optional)
   int fft_len = 0, cp_len = 0, sym_offset = 0;
   float2* d_twiddle = nullptr;
@@ -186,7 +191,9 @@ mamimo_status set_tc_attr(mamimo_engine* e) {
   CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   using Cfg2 = FcTc2Cfg<S>;
   const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
-  CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             FcTc2Cfg<S, true>::kSmemBytes));
   return MAMIMO_OK;
 }
 
@@ -258,7 +265,7 @@ mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
 }
 
 template <int S>
-mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStream_t st) {
+mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStream_t st, const GatherMaps* gm = nullptr) {
   ProfScope ps(e, st, kClsFc);
   if constexpr (S == kFp32Simt) {
     const int grid = ((a.M + 127) / 128) * ((a.N + 127) / 128);
@@ -269,7 +276,12 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
       const int pair_tiles = ((a.M + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((a.N + kTcBN - 1) / kTcBN);
       const int grid2 = 2 * std::min(pair_tiles, e->fc_sms / 2);
       const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
-      fc_tc2_kernel<S><<<grid2, kFcThreads, smem2, st>>>(d.tmap_a, d.tmap_b_half, a);
+      if (gm) {
+        fc_tc2_kernel<S, true><<<grid2, kFcThreads, FcTc2Cfg<S, true>::kSmemBytes, st>>>(d.tmap_a, d.tmap_b_half, *gm, a);
+      } else {
+        static const GatherMaps no_maps = {};
+        fc_tc2_kernel<S, false><<<grid2, kFcThreads, smem2, st>>>(d.tmap_a, d.tmap_b_half, no_maps, a);
+      }
       CK(e, cudaGetLastError());
       e->stats.kernel_launches++;
       return MAMIMO_OK;
@@ -286,9 +298,11 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
 }
 
 // all FC layers of both nets for n_rows rows already staged in act_in[0/1]
+mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps* gm);
+
 template <int S>
 mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, cudaStream_t st,
-                      unsigned net_mask = 3u) {
+                      unsigned net_mask = 3u, bool gather = false) {
   for (int net = 0; net < 2; ++net) {
     if (!(net_mask & (1u << net))) continue;
     for (int l = 0; l < e->n_layers; ++l) {
@@ -310,7 +324,15 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
         a.out_planes = O.ptr; a.out_kpad = e->dl[net][l + 1].K; a.out_plane_rows = O.rows_alloc;
         a.out_scale = e->act_scale;
       }
-      mamimo_status s = launch_fc<S>(e, d, a, st);
+      GatherMaps gm;
+      const bool fused = gather && last;
+      if (fused) {
+        if (S == kFp32Simt || !e->fc_pair) return fail(e, MAMIMO_ERR_UNSUPPORTED, "fused all-gather needs the CTA-pair tensor-core kernel");
+        mamimo_status gs = make_gather_maps(e, net, n_rows, &gm);
+        if (gs != MAMIMO_OK) return gs;
+        a.gather_world = e->gather_world;
+      }
+      mamimo_status s = launch_fc<S>(e, d, a, st, fused ? &gm : nullptr);
       if (s != MAMIMO_OK) return s;
     }
   }
@@ -365,6 +387,29 @@ mamimo_status run_stage_time(mamimo_engine* e, const float* dSr, const float* dS
                                                      e->act_scale, e->d_flags);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
+  }
+  return MAMIMO_OK;
+}
+
+// One map per rank: this rank's row slot inside that rank's gathered plane, clipped to the rows of this call.
+mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps* gm) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (e->gather_world < 1) return fail(e, MAMIMO_ERR_STATE, "fused all-gather not connected (mamimo_gather_connect)");
+  if (n_rows > e->gather_rows) return fail(e, MAMIMO_ERR_INVALID, "more rows than the gather slot holds");
+  const int d_out = e->cfg.d_out;
+  if (d_out % 4) return fail(e, MAMIMO_ERR_UNSUPPORTED, "fused all-gather needs d_out % 4 == 0 (TMA row pitch)");
+  memset(gm, 0, sizeof(*gm));
+  for (int p = 0; p < e->gather_world; ++p) {
+    float* base = e->gather_peer[net][p] + static_cast<size_t>(e->gather_rank) * e->gather_rows * d_out;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_out), static_cast<cuuint64_t>(n_rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_out) * sizeof(float)};
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kFcBlockM)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&gm->m[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (gather) failed: " + std::to_string(r));
   }
   return MAMIMO_OK;
 }
@@ -682,6 +727,7 @@ void mamimo_destroy(mamimo_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
@@ -827,11 +873,16 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   if (!e->finalized) return fail(e, MAMIMO_ERR_STATE, "weights not finalised");
   if (!e->dP) return fail(e, MAMIMO_ERR_STATE, "pilots / P not set (mamimo_set_pilots)");
   const uint32_t all = MAMIMO_STAGE_LS | MAMIMO_STAGE_NET_REAL | MAMIMO_STAGE_NET_IMAG;
+  const bool gather = (stages & MAMIMO_STAGE_GATHER) != 0;
+  stages &= ~MAMIMO_STAGE_GATHER;
   if (stages == 0 || (stages & ~all)) return fail(e, MAMIMO_ERR_INVALID, "bad stage mask");
+  if (gather && (mem != MAMIMO_MEM_DEVICE || n_pkt > e->max_pkts || e->gather_world < 1))
+    return fail(e, MAMIMO_ERR_INVALID, "MAMIMO_STAGE_GATHER needs a connected gather, device buffers and one chunk");
   if (stages != all && (mem != MAMIMO_MEM_DEVICE || n_pkt > e->max_pkts))
     return fail(e, MAMIMO_ERR_INVALID, "partial stage masks need device buffers and n_pkt <= max_pkts (one chunk)");
-  if (n_pkt < 0 || (n_pkt > 0 && (((stages & MAMIMO_STAGE_LS) && !Y) || ((stages & MAMIMO_STAGE_NET_REAL) && !H_real) ||
-                                  ((stages & MAMIMO_STAGE_NET_IMAG) && !H_imag))))
+  if (n_pkt < 0 || (n_pkt > 0 && (((stages & MAMIMO_STAGE_LS) && !Y) ||
+                                  (!gather && (stages & MAMIMO_STAGE_NET_REAL) && !H_real) ||
+                                  (!gather && (stages & MAMIMO_STAGE_NET_IMAG) && !H_imag))))
     return fail(e, MAMIMO_ERR_INVALID, "null buffer");
   if ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(H_ls) | reinterpret_cast<uintptr_t>(H_real) |
        reinterpret_cast<uintptr_t>(H_imag)) & 15)
@@ -847,7 +898,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
     if (s != MAMIMO_OK) return s;
     const unsigned nets = (stages >> 1) & 3u;
     if (!nets) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st, nets)));
+    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st, nets, gather)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
@@ -894,6 +945,62 @@ mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const
   };
   return run_chunked(e, n_pkt, e->max_pkts, sig_real, xb, sig_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_ipc_export(const void* dev_ptr, uint8_t handle[MAMIMO_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == MAMIMO_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (!dev_ptr || !handle || cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)) != cudaSuccess) return MAMIMO_ERR_CUDA;
+  memcpy(handle, &h, sizeof(h));
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_ipc_open(const uint8_t handle[MAMIMO_IPC_HANDLE_BYTES], void** dev_ptr) {
+  cudaIpcMemHandle_t h;
+  if (!handle || !dev_ptr) return MAMIMO_ERR_INVALID;
+  memcpy(&h, handle, sizeof(h));
+  return cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? MAMIMO_OK : MAMIMO_ERR_CUDA;
+}
+
+mamimo_status mamimo_ipc_close(void* dev_ptr) {
+  return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? MAMIMO_OK : MAMIMO_ERR_CUDA;
+}
+
+mamimo_status mamimo_gather_create(mamimo_engine* e, int32_t world, int32_t rank, int64_t pkts_per_rank,
+                                   float** real_plane, float** imag_plane) {
+  if (!e || !real_plane || !imag_plane) return MAMIMO_ERR_INVALID;
+  if (e->n_layers == 0) return fail(e, MAMIMO_ERR_STATE, "no MLP configured");
+  if (world < 1 || world > kMaxGatherRanks || rank < 0 || rank >= world || pkts_per_rank < 1 || pkts_per_rank > e->max_pkts)
+    return fail(e, MAMIMO_ERR_INVALID, "need 1 <= world <= 8, 0 <= rank < world, 1 <= pkts_per_rank <= max_pkts");
+  CK(e, cudaSetDevice(e->cfg.device));
+  e->gather_world = 0;
+  for (int n = 0; n < 2; ++n) { if (e->gather_local[n]) { cudaFree(e->gather_local[n]); e->gather_local[n] = nullptr; } }
+  e->gather_rank = rank;
+  e->gather_rows = pkts_per_rank * e->rows_per_pkt;
+  const size_t bytes = static_cast<size_t>(world) * e->gather_rows * e->cfg.d_out * sizeof(float);
+  for (int n = 0; n < 2; ++n) {
+    CK(e, cudaMalloc(&e->gather_local[n], bytes));
+    CK(e, cudaMemset(e->gather_local[n], 0, bytes));
+  }
+  e->gather_world = -world;                 // allocated, not yet connected
+  *real_plane = e->gather_local[0];
+  *imag_plane = e->gather_local[1];
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, void* const* imag_planes) {
+  if (!e || !real_planes || !imag_planes) return MAMIMO_ERR_INVALID;
+  if (e->gather_world >= 0 && !e->gather_local[0]) return fail(e, MAMIMO_ERR_STATE, "call mamimo_gather_create first");
+  const int world = e->gather_world < 0 ? -e->gather_world : e->gather_world;
+  for (int p = 0; p < world; ++p) {
+    if (!real_planes[p] || !imag_planes[p]) return fail(e, MAMIMO_ERR_INVALID, "null peer plane");
+    e->gather_peer[0][p] = static_cast<float*>(real_planes[p]);
+    e->gather_peer[1][p] = static_cast<float*>(imag_planes[p]);
+  }
+  if (e->gather_peer[0][e->gather_rank] != e->gather_local[0] || e->gather_peer[1][e->gather_rank] != e->gather_local[1])
+    return fail(e, MAMIMO_ERR_INVALID, "entry [rank] must be this engine's own planes");
+  e->gather_world = world;
+  return MAMIMO_OK;
 }
 
 mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len, int32_t sym_offset,

@@ -49,6 +49,7 @@ struct FcArgs {
   const float* A;
   const float* W;
   int kpad;
+  int gather_world;      // fused all-gather (pair kernel, final layer): ranks to store to
 };
 
 constexpr int kFcBlockM = 128;
@@ -318,7 +319,14 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // each SM pulls from L2 are halved (the 1-CTA kernel is L2->SMEM bound: 62 B/clk/SM vs 42 here) and a
 // third pipeline stage fits.  Each CTA keeps the accumulator of its own 128 rows in its own TMEM and
 // drains / stores it exactly like the 1-CTA kernel.
-template <int S>
+// Destination planes of the fused all-gather: one 2-D TMA map per rank, each covering THIS rank's row slot of
+// that rank's gathered plane ([rows of this call][d_out] float32, box 128 rows x 32 columns, SWIZZLE_128B).
+constexpr int kMaxGatherRanks = 8;
+struct GatherMaps {
+  CUtensorMap m[kMaxGatherRanks];
+};
+
+template <int S, bool kGather = false>
 struct FcTc2Cfg {
   using Sch = Scheme<S>;
   static constexpr int BN = 256;
@@ -326,18 +334,26 @@ struct FcTc2Cfg {
   static constexpr int kBBytes = (BN / 2) * 128;             // this CTA's half of the weight tile
   static constexpr int kStageBytes = Sch::kPlanes * (kABytes + kBBytes);
   static constexpr int kAuxBytes = 2048 + 2 * BN * 4;
-  static constexpr int kStagesRaw = (kFcSmemBytes - 1024 - kAuxBytes) / kStageBytes;
+  // gather variant: 2 column halves x 2 ping-pong staging tiles of 128 rows x 128 B for the TMA stores
+  static constexpr int kStoreTileBytes = kFcBlockM * 128;
+  static constexpr int kStoreBytes = kGather ? 4 * kStoreTileBytes : 0;
+  static constexpr int kStagesRaw = (kFcSmemBytes - 1024 - kAuxBytes - kStoreBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kColsPerThread = BN / 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + kStoreBytes + 1024;
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
+  static_assert((kStages * kStageBytes + kAuxBytes) % 1024 == 0, "staging tiles must stay 1024-byte aligned");
 };
 
-template <int S>
+// kGather: final layer only.  Besides (optionally) the local float32 output, every finished 128 x 32 block is
+// staged in shared memory and TMA-stored into the gathered plane of EVERY rank (peer memory over NVLink):
+// the all-gather of H-hat happens inside the kernel that produces it, tile by tile.
+template <int S, bool kGather = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFcThreads, 1)
 fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-              const FcArgs a) {
-  using Cfg = FcTc2Cfg<S>;
+              const __grid_constant__ GatherMaps gm, const FcArgs a) {
+  using Cfg = FcTc2Cfg<S, kGather>;
   using Sch = Scheme<S>;
   constexpr int BN = Cfg::BN;
   constexpr int kStages = Cfg::kStages;
@@ -354,6 +370,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   volatile uint32_t* cta_abort = tmem_slot + 1;
   float* sbias = reinterpret_cast<float*>(aux + 2048);              // [2][BN]
+  uint8_t* store_tiles = aux + Cfg::kAuxBytes;                      // gather only: [half][2][128 rows][128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -500,14 +517,47 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (lane == 0) mbar_arrive_leader(tempty_bar + acc);
       }
       if (!ok) break;
-      const int row = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM + q * 32 + lane;
-      if (row < a.M) {
+      const int row0 = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM;
+      const int row = row0 + q * 32 + lane;
+      if (a.out_planes || a.out_f32) {
+        if (row < a.M) {
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-          const int col = half * Cfg::kColsPerThread + g * 32;
-          fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+          for (int g = 0; g < kGroups; ++g) {
+            const int col = half * Cfg::kColsPerThread + g * 32;
+            fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+          }
         }
       }
+      if constexpr (kGather) {
+        const bool issuer = (q == 0 && lane == 0);          // one thread per column half owns the bulk groups
+        const int r = q * 32 + lane;                        // row inside this CTA's tile
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          uint8_t* tile = store_tiles + (half * 2 + (g & 1)) * Cfg::kStoreTileBytes;
+          if (issuer) tma_store_wait_read<1>();             // the store that last read this tile has drained it
+          named_bar_sync(2 + half, 128);
+          const int col = half * Cfg::kColsPerThread + g * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                     // 8 x 16 B per row, SWIZZLE_128B placement
+            float4 v;
+            v.x = fmaf(sum[g][4 * c + 0], a.alpha, sb[col + 4 * c + 0]);
+            v.y = fmaf(sum[g][4 * c + 1], a.alpha, sb[col + 4 * c + 1]);
+            v.z = fmaf(sum[g][4 * c + 2], a.alpha, sb[col + 4 * c + 2]);
+            v.w = fmaf(sum[g][4 * c + 3], a.alpha, sb[col + 4 * c + 3]);
+            if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2 + half, 128);
+          if (issuer) {
+            for (int p = 0; p < a.gather_world; ++p) tma_store_2d(&gm.m[p], tile, n_blk * BN + col, row0);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if constexpr (kGather) {
+      if (q == 0 && lane == 0) tma_store_wait_all<0>();     // every peer write has left before the CTA retires
     }
     if (ovf) atomicOr(a.flags, kFlagRange);
   }

@@ -141,7 +141,35 @@ class Engine:
                                   C.c_void_p(hr_ptr), C.c_void_p(hi_ptr), mem, C.c_void_p(stream) if stream else None),
               self._h)
 
-    STAGE_LS, STAGE_NET_REAL, STAGE_NET_IMAG = 1, 2, 4
+    STAGE_LS, STAGE_NET_REAL, STAGE_NET_IMAG, STAGE_GATHER = 1, 2, 4, 8
+
+    # ------------------------------------------------------------------ fused all-gather (multi-GPU)
+    def gather_create(self, world, rank, pkts_per_rank):
+        """Allocate this rank's gathered planes; returns their device pointers (real, imag)."""
+        pr, pi = C.c_void_p(), C.c_void_p()
+        check(lib.mamimo_gather_create(self._h, world, rank, pkts_per_rank, C.byref(pr), C.byref(pi)), self._h)
+        self._gather = (world, rank, pkts_per_rank, pr.value, pi.value)
+        return pr.value, pi.value
+
+    def gather_connect(self, real_ptrs, imag_ptrs):
+        """Device pointers of EVERY rank's gathered planes as mapped in this process (entry [rank] = own)."""
+        n = len(real_ptrs)
+        ar = (C.c_void_p * n)(*real_ptrs)
+        ai = (C.c_void_p * n)(*imag_ptrs)
+        check(lib.mamimo_gather_connect(self._h, ar, ai), self._h)
+
+    def gather_planes(self):
+        """This rank's gathered planes as torch CUDA tensors [world * pkts_per_rank * n_rx*n_tx, d_out] (no copy)."""
+        import torch
+        world, rank, ppr, pr, pi = self._gather
+        shape = (world * ppr * self.rows_per_pkt, self.cfg.d_out)
+
+        class _Raw:
+            def __init__(self, ptr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        dev = "cuda:%d" % self.cfg.device
+        return torch.as_tensor(_Raw(pr), device=dev), torch.as_tensor(_Raw(pi), device=dev)
 
     def estimate_stages_raw(self, stages, y_ptr, y_type, n_pkt, hls_ptr, hr_ptr, hi_ptr, stream=0):
         """Piecewise run on device buffers (mamimo_estimate_stages): lets the caller overlap e.g. the all-gather
@@ -309,6 +337,24 @@ class Engine:
         check(lib.mamimo_get_stats(self._h, C.byref(s)), self._h)
         return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes),
                     last_device_flags=int(s.last_device_flags))
+
+
+def ipc_export(dev_ptr):
+    """64-byte CUDA IPC handle of a cudaMalloc'ed device pointer (to send to another process)."""
+    buf = C.create_string_buffer(64)
+    st = lib.mamimo_ipc_export(C.c_void_p(dev_ptr), buf)
+    if st != _capi.OK:
+        raise _capi.MamimoError(st, "cudaIpcGetMemHandle failed")
+    return buf.raw
+
+
+def ipc_open(handle):
+    """Map another process's exported device allocation into this process; returns the device pointer."""
+    p = C.c_void_p()
+    st = lib.mamimo_ipc_open(C.c_char_p(handle), C.byref(p))
+    if st != _capi.OK:
+        raise _capi.MamimoError(st, "cudaIpcOpenMemHandle failed")
+    return p.value
 
 
 # ---------------------------------------------------------------------- integer tables

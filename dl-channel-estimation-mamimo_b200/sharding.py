@@ -87,3 +87,26 @@ class ShardedEstimator:
         for w in works:
             if w is not None:
                 w.wait()
+
+
+def connect_fused_gather(engine, pkts_per_rank, group=None):
+    """One process per GPU: allocate this rank's gathered planes in the engine, exchange CUDA IPC handles over
+    torch.distributed, map every peer's planes and hand them to the engine.  Afterwards
+    engine.estimate_stages_raw(stages | engine.STAGE_GATHER, ...) all-gathers H-hat from inside the final FC
+    kernels.  Returns this rank's gathered planes as torch tensors."""
+    import torch.distributed as dist
+    from .engine import ipc_export, ipc_open
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    pr, pi = engine.gather_create(world, rank, pkts_per_rank)
+    mine = (ipc_export(pr), ipc_export(pi))
+    allh = [None] * world
+    dist.all_gather_object(allh, mine, group=group)
+    reals, imags = [], []
+    for r in range(world):
+        if r == rank:
+            reals.append(pr); imags.append(pi)
+        else:
+            reals.append(ipc_open(allh[r][0])); imags.append(ipc_open(allh[r][1]))
+    engine.gather_connect(reals, imags)
+    dist.barrier(group)
+    return engine.gather_planes()

@@ -168,9 +168,26 @@ MAMIMO_API mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo
 #define MAMIMO_STAGE_LS 1u
 #define MAMIMO_STAGE_NET_REAL 2u
 #define MAMIMO_STAGE_NET_IMAG 4u
+#define MAMIMO_STAGE_GATHER 8u   /* final layers also TMA-store every tile into every rank's gathered plane */
 MAMIMO_API mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_ctype y_type,
                                                 int64_t n_pkt, void* H_ls, float* H_real, float* H_imag,
                                                 mamimo_mem mem, void* stream, uint32_t stages);
+
+/* ---- fused all-gather of H-hat (multi-GPU, one process per GPU) ------------
+ * Each rank owns two gathered planes float32 [world * pkts_per_rank * n_rx*n_tx][d_out] (rank r's rows start at
+ * r * pkts_per_rank * n_rx*n_tx).  gather_create allocates them (cudaMalloc, IPC-exportable) and returns their
+ * device pointers; the host exchanges them (same process: raw pointers; other processes: mamimo_ipc_export /
+ * mamimo_ipc_open) and passes every rank's pair to gather_connect (entry [rank] = this engine's own planes).
+ * Then mamimo_estimate_stages(..., stages | MAMIMO_STAGE_GATHER) makes the final FC layer of each net store
+ * its output tiles into all `world` planes from inside the kernel (TMA stores to peer memory over NVLink);
+ * H_real / H_imag may be NULL.  Peers may read their plane after a cross-rank barrier following the call. */
+#define MAMIMO_IPC_HANDLE_BYTES 64
+MAMIMO_API mamimo_status mamimo_gather_create(mamimo_engine* e, int32_t world, int32_t rank, int64_t pkts_per_rank,
+                                              float** real_plane, float** imag_plane);
+MAMIMO_API mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, void* const* imag_planes);
+MAMIMO_API mamimo_status mamimo_ipc_export(const void* dev_ptr, uint8_t handle[MAMIMO_IPC_HANDLE_BYTES]);
+MAMIMO_API mamimo_status mamimo_ipc_open(const uint8_t handle[MAMIMO_IPC_HANDLE_BYTES], void** dev_ptr);
+MAMIMO_API mamimo_status mamimo_ipc_close(void* dev_ptr);
 
 /* Mode B: rows of caller-supplied planes (float32 [n_rows][d_in]) -> (float32 [n_rows][d_out]) x2.
  * This is what CSIPredictor.inference does with X.real / X.imag (inference.py:29-30). */

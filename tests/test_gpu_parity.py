@@ -425,3 +425,51 @@ def test_estimate_from_time_domain_reference_numerology():
     ref_ls, ref_r, ref_i = oracle_full(Yref, tables.sylvester_hadamard(nt), xp, 1, nets)
     assert rel_l2(ref_ls, Hls) <= 3e-6
     assert rel_l2(ref_r + 1j * ref_i, Hr.astype(np.float64) + 1j * Hi) <= TOL_DNN
+
+
+# ------------------------------------------------------------------------------ fused all-gather (final FC layer -> peers)
+@pytest.mark.parametrize("nt,nr,nsc,hidden,pkts", [(8, 2, 128, (128, 64), (5, 3)), (32, 4, 1024, (1024, 1024), (3, 3))])
+def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts):
+    """Two engines on one GPU act as two ranks: each runs the path on its packet shard with MAMIMO_STAGE_GATHER and
+    the final FC kernels TMA-store every tile into BOTH ranks' gathered planes.  Both planes must equal the
+    unsharded result bit for bit (rank r's rows at r * pkts_per_rank * Nt*Nr)."""
+    import torch
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    npkt = sum(pkts)
+    ppr = max(pkts)
+    Y, _ = mm.synth.make_packets(10, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    rows = nt * nr
+    engs = []
+    try:
+        for r in range(2):
+            e = mm.Engine(nt, nr, nsc, hidden=hidden, precision="fp16x3")
+            e.set_pilots(x, None)
+            e.load_weights(nets)
+            engs.append(e)
+        ref_r, ref_i = engs[0].estimate(Y)                      # unsharded reference on the same kernels
+        ptrs = [e.gather_create(2, r, ppr) for r, e in enumerate(engs)]
+        for e in engs:
+            e.gather_connect([p[0] for p in ptrs], [p[1] for p in ptrs])
+        st = torch.cuda.current_stream().cuda_stream
+        lo = 0
+        for r, e in enumerate(engs):
+            Yd = torch.from_numpy(Y[lo:lo + pkts[r]]).cuda()
+            e.estimate_stages_raw(e.STAGE_LS | e.STAGE_NET_REAL | e.STAGE_NET_IMAG | e.STAGE_GATHER, Yd.data_ptr(), 0,
+                                  pkts[r], 0, 0, 0, st)
+            lo += pkts[r]
+        torch.cuda.synchronize()
+        for e in engs:
+            gr, gi = e.gather_planes()
+            gr, gi = gr.cpu().numpy(), gi.cpu().numpy()
+            lo = 0
+            for r in range(2):
+                sl = slice(r * ppr * rows, (r * ppr + pkts[r]) * rows)
+                assert np.array_equal(gr[sl], ref_r[lo * rows:(lo + pkts[r]) * rows])
+                assert np.array_equal(gi[sl], ref_i[lo * rows:(lo + pkts[r]) * rows])
+                # rows of the slot beyond this rank's packets stay untouched (zero): TMA clipped the tile
+                assert not gr[(r * ppr + pkts[r]) * rows:(r + 1) * ppr * rows].any()
+                lo += pkts[r]
+    finally:
+        for e in engs:
+            e.close()
