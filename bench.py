@@ -198,8 +198,19 @@ def run_ours(args):
     #  --gather nccl: NCCL all-gather of each plane; the real plane's gather overlaps the imaginary net and the
     #      FC kernels leave --sm-reserve SMs free so the NCCL kernel never blocks a persistent CTA.
     fused = world > 1 and args.gather == "fused"
+    gather_note = args.gather
     if fused:
-        g_real, g_imag = mm.sharding.connect_fused_gather(eng, npkt)
+        try:
+            g_real, g_imag = mm.sharding.connect_fused_gather(eng, npkt)
+            okf = torch.ones(1, device=dev)
+        except Exception as ex:                       # e.g. CUDA IPC / peer access unavailable on this box
+            okf = torch.zeros(1, device=dev)
+            gather_note = "nccl (fused unavailable: %s)" % str(ex)[:80]
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)     # every rank must take the same path
+        if okf.item() == 0:
+            fused = False
+            if gather_note == "fused":
+                gather_note = "nccl (fused unavailable on a peer)"
         flag = torch.zeros(1, device=dev)
     ALL = eng.STAGE_LS | eng.STAGE_NET_REAL | eng.STAGE_NET_IMAG
 
@@ -296,15 +307,24 @@ def run_ours(args):
     fc_ms_per_step = prof["fc_ms"] / args.steps
     ls_ms_per_step = prof["ls_ms"] / args.steps
     fc_tflops = MLP_FLOP_PER_PKT * npkt / (fc_ms_per_step * 1e-3) / 1e12 if fc_ms_per_step > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "fc_tc_kernel" if args.precision != "fp32_simt" else "fc_simt_kernel",
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    fc_name = "fc_tc2_kernel" if args.precision != "fp32_simt" else "fc_simt_kernel"
+    roofline = {"bound": "tensor", "kernel": fc_name,
                 "achieved": fc_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": fc_tflops / peaks["bf16_tflops"], "peak_source": peak_src + " bf16 burst (cuBLAS)",
-                "traffic": None, "avg_launch_ms": prof["fc_ms"] / max(1, prof["fc_launches"]),
+                "traffic": (traffic.get(fc_name, {}).get("bytes_per_launch") if args.precision == "fp16x3" and npkt == 500 else None),
+                "traffic_unit": "bytes/launch (ncu dram read+write)", "flop_per_launch": MLP_FLOP_PER_PKT * npkt / 6,
+                "avg_launch_ms": prof["fc_ms"] / max(1, prof["fc_launches"]),
                 "share_of_step": fc_ms_per_step / ms_step if ms_step > 0 else None,
                 "mma_passes": {"tf32x3": 3, "fp16x3": 3, "bf16x1": 1, "fp32_simt": 0}[args.precision]}
     ls_gbs = LS_BYTES_PER_PKT * npkt / (ls_ms_per_step * 1e-3) / 1e9 if ls_ms_per_step > 0 else 0.0
     roofline_ls = {"bound": "hbm", "kernel": "ls_kernel", "achieved": ls_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": ls_gbs / peaks["hbm_gbs"], "avg_launch_ms": prof["ls_ms"] / max(1, prof["ls_launches"]),
+                   "traffic": (traffic.get("ls_kernel", {}).get("bytes_per_launch") if args.precision == "fp16x3" and npkt == 500 else None),
+                   "bytes_per_launch": LS_BYTES_PER_PKT * npkt,
                    "note": "algorithmic bytes = Y in + one operand-plane set out (2 MiB/packet)"}
 
     cpu_baseline = None
@@ -324,7 +344,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "pkts_per_gpu": npkt, "precision": args.precision,
                        "l2": "inputs (0.5 GiB Y) and outputs (0.5 GiB) per step exceed the 126 MB L2",
                        "parallelism": "packets sharded over %d GPU(s)%s" % (
-                           world, (", all-gather of H planes in step (%s)" % args.gather) if world > 1 else "")},
+                           world, (", all-gather of H planes in step (%s)" % gather_note) if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
                     "d2h_bytes_per_step": int(2 * rows * NSC * 4), "checksum": checksum},

@@ -158,8 +158,10 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
   if (a.n_ps == 1 && (nk & 3) == 0 && (a.n_sc & 3) == 0 && (a.kpad & 3) == 0) {
     // fast path (every reference call site): 4 consecutive tones per thread, 8/16/32-byte stores
     const int nq = nk >> 2;
+    const int lg = 31 - __clz(nq);                       // tiles are 128 tones: nq = 32, shifts instead of a division
+    const bool pow2 = (nq & (nq - 1)) == 0;
     for (int idx = threadIdx.x; idx < a.n_tx * nq; idx += blockDim.x) {
-      const int j = idx / nq;
+      const int j = pow2 ? (idx >> lg) : (idx / nq);
       const int kk = (idx - j * nq) << 2;
       const float4 v01 = *reinterpret_cast<const float4*>(sh + j * pitch + kk);
       const float4 v23 = *reinterpret_cast<const float4*>(sh + j * pitch + kk + 2);
