@@ -70,6 +70,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  int l2_prefetch = 1;
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
@@ -315,6 +316,7 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
       a.a_plane_rows = A.rows_alloc; a.b_plane_rows = d.w.rows_alloc;
       a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = last ? 0 : 1;
       a.flags = e->d_flags;
+      a.l2_prefetch = e->l2_prefetch;
       a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
       if (last) {
         a.out_f32 = net == 0 ? out_r : out_i;
@@ -675,6 +677,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
   if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }
   e->rows_alloc = round_up(static_cast<int>(rows), 256);   // whole CTA-pair row tiles

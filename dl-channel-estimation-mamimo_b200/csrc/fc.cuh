@@ -50,6 +50,7 @@ struct FcArgs {
   const float* W;
   int kpad;
   int gather_world;      // fused all-gather (pair kernel, final layer): ranks to store to
+  int l2_prefetch;       // pair kernel: prefetch the next tile's activation rows into L2
 };
 
 constexpr int kFcBlockM = 128;
@@ -419,9 +420,19 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
           const int row0 = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM;        // this CTA's activation rows
           const int wrow0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);           // this CTA's weight rows
+          // the next tile of this cluster touches other activation rows (tiles are 74 apart): pull them into L2
+          // now, so its loads never see HBM latency (3 stages only cover ~2 stage-times of lookahead)
+          const int next_tile = tile + n_clusters;
+          const int next_row0 = next_tile < total_tiles
+                                    ? ((next_tile / n_tiles) * 2 + static_cast<int>(cta_rank)) * kFcBlockM : -1;
           for (int kb = 0; kb < a.num_k_blocks; ++kb) {
             if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
             uint8_t* st = smem + stage * Cfg::kStageBytes;
+            if (next_row0 >= 0 && a.l2_prefetch) {
+#pragma unroll
+              for (int p = 0; p < kPlanes; ++p)
+                tma_prefetch_l2_2d(&tmap_a, kb * Sch::kBlockK, p * a.a_plane_rows + next_row0);
+            }
             if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);
 #pragma unroll
             for (int p = 0; p < kPlanes; ++p)
