@@ -70,7 +70,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
-  int l2_prefetch = 1;
+  int l2_prefetch = 0;             // measured slower (426 vs 442 TFLOP/s): kept as an experiment knob (MAMIMO_L2_PREFETCH)
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
