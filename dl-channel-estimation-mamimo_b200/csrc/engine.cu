@@ -84,7 +84,7 @@ struct mamimo_engine {
   HostLayer hl[2][MAMIMO_MAX_HIDDEN + 1];
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
-  Operand act_h[2];             // ping-pong hidden activations (shared by both nets)
+  Operand act_h[2][2];          // [net][ping-pong] hidden activations (per net, so the nets can overlap)
   // fused all-gather (optional): gathered planes [world * gather_rows][d_out] float32 per rank
   int gather_world = 0, gather_rank = 0;
   int64_t gather_rows = 0;                 // rows per rank slot
@@ -98,7 +98,9 @@ struct mamimo_engine {
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;  // pinned
   // host-memory pipeline
-  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_side = nullptr;
+  cudaEvent_t ev_side[2] = {nullptr, nullptr};
+  int gather_sms = 0;           // > 0: SMs given to the real net's gathering layer while the imaginary net computes
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   void* st_in[2] = {nullptr, nullptr};
   size_t st_in_bytes = 0;
@@ -303,12 +305,13 @@ mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps
 
 template <int S>
 mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, cudaStream_t st,
-                      unsigned net_mask = 3u, bool gather = false) {
+                      unsigned net_mask = 3u, bool gather = false, int l_begin = 0, int l_end = -1) {
+  if (l_end < 0) l_end = e->n_layers;
   for (int net = 0; net < 2; ++net) {
     if (!(net_mask & (1u << net))) continue;
-    for (int l = 0; l < e->n_layers; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {
       const DevLayer& d = e->dl[net][l];
-      const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
+      const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[net][(l - 1) & 1];
       const bool last = (l == e->n_layers - 1);
       FcArgs a;
       memset(&a, 0, sizeof(a));
@@ -322,7 +325,7 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
         a.out_f32 = net == 0 ? out_r : out_i;
         a.out_ld = d.N;
       } else {
-        const Operand& O = e->act_h[l & 1];
+        const Operand& O = e->act_h[net][l & 1];
         a.out_planes = O.ptr; a.out_kpad = e->dl[net][l + 1].K; a.out_plane_rows = O.rows_alloc;
         a.out_scale = e->act_scale;
       }
@@ -689,6 +692,8 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   ck(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), "stream");
   ck(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), "stream");
   ck(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), "stream");
+  ck(cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking), "stream");
+  for (int i = 0; i < 2; ++i) ck(cudaEventCreateWithFlags(&e->ev_side[i], cudaEventDisableTiming), "event");
   for (int i = 0; i < 2; ++i) {
     ck(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming), "event");
     ck(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming), "event");
@@ -703,7 +708,8 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
     for (int net = 0; net < 2 && s == MAMIMO_OK; ++net) s = alloc_operand(e, e->act_in[net], e->planes, e->rows_alloc, kin, e->elem_bytes);
     if (cfg->n_hidden > 0)
       for (int i = 0; i < (cfg->n_hidden > 1 ? 2 : 1) && s == MAMIMO_OK; ++i)
-        s = alloc_operand(e, e->act_h[i], e->planes, e->rows_alloc, kh, e->elem_bytes);
+        for (int net = 0; net < 2 && s == MAMIMO_OK; ++net)
+          s = alloc_operand(e, e->act_h[net][i], e->planes, e->rows_alloc, kh, e->elem_bytes);
     if (s != MAMIMO_OK) return bail(s);
     int in = cfg->d_in;
     for (int l = 0; l <= cfg->n_hidden; ++l) {
@@ -738,7 +744,7 @@ void mamimo_destroy(mamimo_engine* e) {
     for (int l = 0; l <= MAMIMO_MAX_HIDDEN; ++l) { fr(e->dl[net][l].w.ptr); fr(e->dl[net][l].bias); }
   }
   for (int i = 0; i < 2; ++i) {
-    fr(e->act_h[i].ptr); fr(e->st_in[i]); fr(e->st_in2[i]); fr(e->st_hr[i]); fr(e->st_hi[i]); fr(e->st_hls[i]);
+    fr(e->act_h[0][i].ptr); fr(e->act_h[1][i].ptr); fr(e->st_in[i]); fr(e->st_in2[i]); fr(e->st_hr[i]); fr(e->st_hi[i]); fr(e->st_hls[i]);
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
     if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
     if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
@@ -746,6 +752,8 @@ void mamimo_destroy(mamimo_engine* e) {
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  if (e->s_side) cudaStreamDestroy(e->s_side);
+  for (int i = 0; i < 2; ++i) if (e->ev_side[i]) cudaEventDestroy(e->ev_side[i]);
   delete e;
 }
 
@@ -841,7 +849,7 @@ mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
         if (s != MAMIMO_OK) return s;
         s = make_map(e, &d.tmap_b_half, d.w, d.w.kpad, kTcBN / 2);
         if (s != MAMIMO_OK) return s;
-        const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[(l - 1) & 1];
+        const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[net][(l - 1) & 1];
         s = make_map(e, &d.tmap_a, A, d.K, kFcBlockM);
         if (s != MAMIMO_OK) return s;
       }
@@ -901,7 +909,27 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
     if (s != MAMIMO_OK) return s;
     const unsigned nets = (stages >> 1) & 3u;
     if (!nets) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st, nets, gather)));
+    const int rows = static_cast<int>(n) * e->rows_per_pkt;
+    const int L = e->n_layers;
+    if (gather && nets == 3u && e->gather_sms > 0 && L >= 2) {
+      // NVLink-bound regime (world >= 4): the real net's gathering final layer runs on a side stream with a
+      // few SMs (it only has to keep NVLink busy) while the imaginary net's hidden layers use the rest.
+      const int full = e->fc_sms;
+      s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 1u, false, 0, L - 1)));
+      if (s != MAMIMO_OK) return s;
+      CK(e, cudaEventRecord(e->ev_side[0], st));
+      CK(e, cudaStreamWaitEvent(e->s_side, e->ev_side[0], 0));
+      e->fc_sms = e->gather_sms;
+      s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, e->s_side, 1u, true, L - 1, L)));
+      e->fc_sms = full - e->gather_sms;
+      if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 2u, false, 0, L - 1)));
+      e->fc_sms = full;
+      if (s != MAMIMO_OK) return s;
+      CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
+      CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
+      return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 2u, true, L - 1, L)));
+    }
+    return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, nets, gather)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
@@ -1003,6 +1031,11 @@ mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, 
   if (e->gather_peer[0][e->gather_rank] != e->gather_local[0] || e->gather_peer[1][e->gather_rank] != e->gather_local[1])
     return fail(e, MAMIMO_ERR_INVALID, "entry [rank] must be this engine's own planes");
   e->gather_world = world;
+  // world >= 4: a plane's NVLink time exceeds a layer's compute time -> overlap it with the other net (see
+  // mamimo_estimate_stages).  The gathering layer only needs enough SMs to keep NVLink busy.
+  e->gather_sms = world >= 6 ? 36 : (world >= 3 ? 56 : 0);
+  if (const char* env = getenv("MAMIMO_GATHER_SMS")) e->gather_sms = atoi(env) & ~1;
+  if (e->gather_sms >= e->fc_sms - 2) e->gather_sms = 0;
   return MAMIMO_OK;
 }
 

@@ -428,12 +428,16 @@ def test_estimate_from_time_domain_reference_numerology():
 
 
 # ------------------------------------------------------------------------------ fused all-gather (final FC layer -> peers)
+@pytest.mark.parametrize("gather_sms", [0, 36])
 @pytest.mark.parametrize("nt,nr,nsc,hidden,pkts", [(8, 2, 128, (128, 64), (5, 3)), (32, 4, 1024, (1024, 1024), (3, 3))])
-def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts):
+def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sms, monkeypatch):
     """Two engines on one GPU act as two ranks: each runs the path on its packet shard with MAMIMO_STAGE_GATHER and
     the final FC kernels TMA-store every tile into BOTH ranks' gathered planes.  Both planes must equal the
     unsharded result bit for bit (rank r's rows at r * pkts_per_rank * Nt*Nr)."""
     import torch
+    # gather_sms > 0 forces the NVLink-bound schedule (real net's gathering layer on a side stream with few SMs,
+    # concurrent with the imaginary net's hidden layers) that the engine picks by itself for world >= 3
+    monkeypatch.setenv("MAMIMO_GATHER_SMS", str(gather_sms))
     x = mm.synth.make_pilots(nsc)
     nets = mm.synth.make_nets(nsc, hidden, nsc)
     npkt = sum(pkts)
