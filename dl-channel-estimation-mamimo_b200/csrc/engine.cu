@@ -70,6 +70,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  unsigned long long* d_dbg = nullptr;   // MAMIMO_FC_DEBUG=1: role wait-cycle counters of the pair kernel
   int l2_prefetch = 0;             // measured slower (426 vs 442 TFLOP/s): kept as an experiment knob (MAMIMO_L2_PREFETCH)
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
   int n_pil = 0;
@@ -320,6 +321,7 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
       a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = last ? 0 : 1;
       a.flags = e->d_flags;
       a.l2_prefetch = e->l2_prefetch;
+      a.dbg = e->d_dbg;
       a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
       if (last) {
         a.out_f32 = net == 0 ? out_r : out_i;
@@ -681,6 +683,10 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
+  if (const char* env = getenv("MAMIMO_FC_DEBUG")) {
+    if (atoi(env) && cudaMalloc(&e->d_dbg, 8 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(e->d_dbg, 0, 8 * sizeof(unsigned long long));
+  }
   const long long rows = static_cast<long long>(e->max_pkts) * rows_per_unit;
   if (rows > (1ll << 30)) { e->err = "max_pkts too large"; return bail(MAMIMO_ERR_INVALID); }
   e->rows_alloc = round_up(static_cast<int>(rows), 256);   // whole CTA-pair row tiles
@@ -735,6 +741,14 @@ void mamimo_destroy(mamimo_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
+  if (e->d_dbg) {          // diagnostic dump: average cycles per cluster over the engine's lifetime
+    unsigned long long h[8] = {0};
+    cudaMemcpy(h, e->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const double n = h[5] ? static_cast<double>(h[5]) : 1.0;
+    fprintf(stderr, "[mamimo fc debug] per cluster-launch: producer wait-empty %.0f of %.0f cyc | MMA wait-tmem %.0f, wait-operands %.0f of %.0f cyc (%llu cluster-launches)\n",
+            h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5]);
+    cudaFree(e->d_dbg);
+  }
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_bins); fr(e->d_ydemod);

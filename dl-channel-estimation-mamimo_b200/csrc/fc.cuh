@@ -51,6 +51,7 @@ struct FcArgs {
   int kpad;
   int gather_world;      // fused all-gather (pair kernel, final layer): ranks to store to
   int l2_prefetch;       // pair kernel: prefetch the next tile's activation rows into L2
+  unsigned long long* dbg;  // optional [8]: cycles the pair kernel's roles spent waiting (MAMIMO_FC_DEBUG=1)
 };
 
 constexpr int kFcBlockM = 128;
@@ -416,6 +417,8 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         bool ok = true;
+        long long dbg_wait = 0;
+        const long long dbg_t0 = a.dbg ? clock64() : 0;
         for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
           const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
           const int row0 = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM;        // this CTA's activation rows
@@ -426,7 +429,9 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const int next_row0 = next_tile < total_tiles
                                     ? ((next_tile / n_tiles) * 2 + static_cast<int>(cta_rank)) * kFcBlockM : -1;
           for (int kb = 0; kb < a.num_k_blocks; ++kb) {
+            const long long t_w = a.dbg ? clock64() : 0;
             if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            if (a.dbg) dbg_wait += clock64() - t_w;
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             if (next_row0 >= 0 && a.l2_prefetch) {
 #pragma unroll
@@ -445,6 +450,10 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (a.dbg && leader) {
+          atomicAdd(a.dbg + 0, static_cast<unsigned long long>(dbg_wait));              // producer: waiting for a free stage
+          atomicAdd(a.dbg + 1, static_cast<unsigned long long>(clock64() - dbg_t0));    // producer: total
+        }
       }
     } else if (warp == 1 && leader) {
       // ================= MMA issuer (one thread of the leader CTA) =================
@@ -454,16 +463,22 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         uint32_t phase = 0;
         bool ok = true;
         uint32_t unit = 0;
+        long long w_tempty = 0, w_full = 0;
+        const long long dbg_t0 = a.dbg ? clock64() : 0;
         for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
           for (int c = 0; c < n_chunks && ok; ++c, ++unit) {
             const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+            const long long t_e = a.dbg ? clock64() : 0;
             if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
+            if (a.dbg) w_tempty += clock64() - t_e;
             tc_fence_after_sync();
             const uint32_t tmem_d = tmem_base + acc * BN;
             const int kb_end = min(a.num_k_blocks, (c + 1) * kbc);
             uint32_t fresh = 1;
             for (int kb = c * kbc; kb < kb_end; ++kb) {
+              const long long t_f = a.dbg ? clock64() : 0;
               if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
+              if (a.dbg) w_full += clock64() - t_f;
               tc_fence_after_sync();
               const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
               const uint32_t sb = sa + kPlanes * Cfg::kABytes;
@@ -482,6 +497,12 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             }
             if (ok) umma_commit_pair(tfull_bar + acc, 3);   // both CTAs' epilogues may drain
           }
+        }
+        if (a.dbg) {
+          atomicAdd(a.dbg + 2, static_cast<unsigned long long>(w_tempty));               // MMA: waiting for a drained TMEM buffer
+          atomicAdd(a.dbg + 3, static_cast<unsigned long long>(w_full));                 // MMA: waiting for operands
+          atomicAdd(a.dbg + 4, static_cast<unsigned long long>(clock64() - dbg_t0));     // MMA: total
+          atomicAdd(a.dbg + 5, 1ull);                                                    // clusters counted
         }
       }
     }
