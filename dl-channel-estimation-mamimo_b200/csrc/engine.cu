@@ -86,6 +86,12 @@ struct mamimo_engine {
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
   Operand act_h[2][2];          // [net][ping-pong] hidden activations (per net, so the nets can overlap)
+  // mode A with the de-duplicated first layer (see expand_pairs_kernel)
+  bool dedup_a = false;
+  float* d_z[2] = {nullptr, nullptr};        // [n_prx][h0] first-layer LTF term
+  float* d_T[2] = {nullptr, nullptr};        // [n_tx][h0]  W1_p^T p_j + b1
+  float* d_zero_bias = nullptr;              // [h0] zeros (the bias rides in T)
+  std::vector<double> hW0p[2], hb0[2];       // host copies to rebuild T when P changes
   // fused all-gather (optional): gathered planes [world * gather_rows][d_out] float32 per rank
   int gather_world = 0, gather_rank = 0;
   int64_t gather_rows = 0;                 // rows per rank slot
@@ -396,6 +402,70 @@ mamimo_status run_stage_time(mamimo_engine* e, const float* dSr, const float* dS
     e->stats.kernel_launches++;
   }
   return MAMIMO_OK;
+}
+
+// Mode A with the de-duplicated first layer: T[j][n] = b1[n] + sum_m Re P[j][m] * W1[len_ltf + m][n]
+// (the generator feeds P(:, iTx) of the pickled P = row j of the MATLAB-oriented P held here).
+mamimo_status rebuild_mode_a_table(mamimo_engine* e) {
+  if (!e->dedup_a || e->hW0p[0].empty()) return MAMIMO_OK;
+  const int nt = e->cfg.n_tx, nl = e->cfg.n_ltf, h0 = e->cfg.hidden[0];
+  if (e->hP.empty()) return fail(e, MAMIMO_ERR_STATE, "P not set (mamimo_set_pilots)");
+  std::vector<float> T(static_cast<size_t>(nt) * h0);
+  for (int net = 0; net < 2; ++net) {
+    for (int j = 0; j < nt; ++j)
+      for (int n = 0; n < h0; ++n) {
+        double acc = e->hb0[net][n];
+        for (int m = 0; m < nt; ++m)
+          acc += static_cast<double>(e->hP[2 * (j * nl + m)]) * e->hW0p[net][static_cast<size_t>(m) * h0 + n];
+        T[static_cast<size_t>(j) * h0 + n] = static_cast<float>(acc);
+      }
+    CK(e, cudaMemcpy(e->d_T[net], T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return MAMIMO_OK;
+}
+
+// rows of this chunk: LTF planes per (pkt, rx) -> Z = X_ltf W1_ltf^T (one GEMM per net, n_pkt*n_rx rows) ->
+// expand to pair rows with relu(Z + T) -> remaining layers on n_pkt*n_rx*n_tx rows
+template <int S>
+mamimo_status run_mode_a_dedup(mamimo_engine* e, const float* dSr, const float* dSi, int64_t n_pkt, float* hr,
+                               float* hi, cudaStream_t st) {
+  const int64_t n_prx = n_pkt * e->cfg.n_rx;
+  const int h0 = e->cfg.hidden[0];
+  const int threads = 256;
+  for (int net = 0; net < 2; ++net) {
+    const Operand& A = e->act_in[net];
+    {
+      const int64_t total = n_prx * e->cfg.len_ltf;
+      const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
+      ProfScope ps(e, st, kClsStage);
+      stage_planes_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dSr : dSi, A.ptr, n_prx, e->cfg.len_ltf, A.rows_alloc,
+                                                       A.kpad, e->act_scale, e->d_flags);
+    }
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    const DevLayer& d = e->dl[net][0];
+    FcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = static_cast<int>(n_prx); a.N = d.N; a.num_k_blocks = d.K / e->block_k; a.kb_per_chunk = e->kb_per_chunk;
+    a.a_plane_rows = A.rows_alloc; a.b_plane_rows = d.w.rows_alloc;
+    a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = 0;
+    a.flags = e->d_flags; a.dbg = e->d_dbg;
+    a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
+    a.out_f32 = e->d_z[net]; a.out_ld = h0;
+    mamimo_status s = launch_fc<S>(e, d, a, st);
+    if (s != MAMIMO_OK) return s;
+    const Operand& O = e->act_h[net][0];
+    {
+      const int64_t total = n_prx * e->cfg.n_tx * (e->dl[net][1].K / 4);
+      const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
+      ProfScope ps(e, st, kClsStage);
+      expand_pairs_kernel<S><<<grid, threads, 0, st>>>(e->d_z[net], e->d_T[net], O.ptr, n_prx, e->cfg.n_tx, h0,
+                                                       O.rows_alloc, e->dl[net][1].K, e->act_scale, e->d_flags);
+    }
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  return run_mlp<S>(e, static_cast<int>(n_prx) * e->cfg.n_tx, hr, hi, st, 3u, false, 1, e->n_layers);
 }
 
 // One map per rank: this rank's row slot inside that rank's gathered plane, clipped to the rows of this call.
@@ -711,7 +781,21 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
     const int kin = round_up(cfg->d_in, e->block_k);
     int kh = e->block_k;
     for (int i = 0; i < cfg->n_hidden; ++i) kh = std::max(kh, round_up(cfg->hidden[i], e->block_k));
-    for (int net = 0; net < 2 && s == MAMIMO_OK; ++net) s = alloc_operand(e, e->act_in[net], e->planes, e->rows_alloc, kin, e->elem_bytes);
+    // mode A: the first layer runs once per (pkt, rx) on the LTF part only when there is a hidden layer to expand into
+    e->dedup_a = cfg->input_mode == MAMIMO_INPUT_TIME_P && cfg->n_hidden >= 1 && (cfg->hidden[0] % 4) == 0 &&
+                 getenv("MAMIMO_NO_DEDUP") == nullptr;
+    const int in_rows = e->dedup_a ? round_up(e->max_pkts * cfg->n_rx, 256) : e->rows_alloc;
+    const int in_k = e->dedup_a ? round_up(cfg->len_ltf, e->block_k) : kin;
+    for (int net = 0; net < 2 && s == MAMIMO_OK; ++net) s = alloc_operand(e, e->act_in[net], e->planes, in_rows, in_k, e->elem_bytes);
+    if (e->dedup_a && s == MAMIMO_OK) {
+      const size_t h0 = cfg->hidden[0];
+      for (int net = 0; net < 2; ++net) {
+        ck(cudaMalloc(&e->d_z[net], static_cast<size_t>(in_rows) * h0 * sizeof(float)), "cudaMalloc z");
+        ck(cudaMalloc(&e->d_T[net], static_cast<size_t>(cfg->n_tx) * h0 * sizeof(float)), "cudaMalloc T");
+      }
+      ck(cudaMalloc(&e->d_zero_bias, h0 * sizeof(float)), "cudaMalloc zero bias");
+      if (s == MAMIMO_OK) ck(cudaMemset(e->d_zero_bias, 0, h0 * sizeof(float)), "memset zero bias");
+    }
     if (cfg->n_hidden > 0)
       for (int i = 0; i < (cfg->n_hidden > 1 ? 2 : 1) && s == MAMIMO_OK; ++i)
         for (int net = 0; net < 2 && s == MAMIMO_OK; ++net)
@@ -751,6 +835,7 @@ void mamimo_destroy(mamimo_engine* e) {
   }
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
+  fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
   fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
@@ -801,6 +886,7 @@ mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const fl
   if (!e->d_inv_den) CK(e, cudaMalloc(&e->d_inv_den, inv.size() * sizeof(float)));
   CK(e, cudaMemcpy(e->dP, e->hP.data(), e->hP.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(e, cudaMemcpy(e->d_inv_den, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (e->finalized) return rebuild_mode_a_table(e);       // mode A: the P-row term of the first layer depends on P
   return MAMIMO_OK;
 }
 
@@ -856,7 +942,16 @@ mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
       DevLayer& d = e->dl[net][l];
       if (d.w.ptr) { cudaFree(d.w.ptr); d.w.ptr = nullptr; }
       if (d.bias) { cudaFree(d.bias); d.bias = nullptr; }
-      mamimo_status s = DISPATCH_S(e, (upload_layer<S>(e, d, Wf, bf, L.in, L.out)));
+      int in_used = L.in;
+      if (l == 0 && e->dedup_a) {
+        // keep only the LTF rows of the first kernel in the GEMM; the P-row rows and the bias go into the table T
+        in_used = e->cfg.len_ltf;
+        e->hW0p[net].assign(Wf.begin() + static_cast<size_t>(in_used) * L.out, Wf.end());   // [n_tx][h0]
+        e->hb0[net] = bf;
+        Wf.resize(static_cast<size_t>(in_used) * L.out);
+        std::fill(bf.begin(), bf.end(), 0.0);
+      }
+      mamimo_status s = DISPATCH_S(e, (upload_layer<S>(e, d, Wf, bf, in_used, L.out)));
       if (s != MAMIMO_OK) return s;
       if (e->cfg.precision != MAMIMO_PREC_FP32_SIMT) {
         s = make_map(e, &d.tmap_b, d.w, d.w.kpad, kTcBN);
@@ -868,6 +963,10 @@ mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
         if (s != MAMIMO_OK) return s;
       }
     }
+  }
+  {
+    mamimo_status ts = rebuild_mode_a_table(e);
+    if (ts != MAMIMO_OK) return ts;
   }
   e->finalized = true;
   return MAMIMO_OK;
@@ -984,6 +1083,8 @@ mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const
   const size_t xb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.len_ltf * sizeof(float);
   const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
   auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
+    if (e->dedup_a)
+      return DISPATCH_S(e, (run_mode_a_dedup<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, hr, hi, st)));
     mamimo_status s = DISPATCH_S(e, (run_stage_time<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
     if (s != MAMIMO_OK) return s;
     return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));

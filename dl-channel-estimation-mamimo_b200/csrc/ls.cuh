@@ -291,4 +291,49 @@ __global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2*
   if (ovf) atomicOr(flags, kFlagRange);
 }
 
+// ---- mode A, de-duplicated first layer --------------------------------------------------------------------
+// The LTF part of the first-layer input is identical for the Nt pairs of one (pkt, rx) -- the reference itself
+// stores it once per rx under a hash (create_massiveMIMO_CSIest_dnn_dataset.py:50-59) -- so
+//   W1^T [x_ltf || p_j] + b1 = (W1_ltf^T x_ltf) + (W1_p^T p_j + b1) = Z[prx] + T[j].
+// Z comes from one GEMM over n_pkt*n_rx rows (32x fewer first-layer FLOPs); this kernel expands it to the
+// n_pkt*n_rx*n_tx pair rows: relu(Z[prx] + T[j]) -> split operand planes of the second layer.
+template <int S>
+__global__ void expand_pairs_kernel(const float* __restrict__ Z, const float* __restrict__ T, void* planes,
+                                    int64_t n_prx, int n_tx, int h, int plane_rows, int kpad, float scale,
+                                    uint32_t* flags) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  bool ovf = false;
+  const int hq = kpad >> 2;                                // h % 4 == 0 (checked on the host); pad columns get zeros
+  const int64_t total = n_prx * n_tx * hq;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / hq;
+    const int n = static_cast<int>(i - r * hq) << 2;
+    const int64_t prx = r / n_tx;
+    const int j = static_cast<int>(r - prx * n_tx);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f), t = z;
+    if (n < h) {
+      z = __ldg(reinterpret_cast<const float4*>(Z + prx * h + n));
+      t = __ldg(reinterpret_cast<const float4*>(T + static_cast<size_t>(j) * h + n));
+    }
+    const float v[4] = {fmaxf(z.x + t.x, 0.f), fmaxf(z.y + t.y, 0.f), fmaxf(z.z + t.z, 0.f), fmaxf(z.w + t.w, 0.f)};
+    E p[4][Sch::kPlanes];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Sch::split(v[q], scale, p[q], &ovf);
+#pragma unroll
+    for (int pl = 0; pl < Sch::kPlanes; ++pl) {
+      E* d = reinterpret_cast<E*>(planes) + (static_cast<size_t>(pl) * plane_rows + r) * kpad + n;
+      if constexpr (sizeof(E) == 4) {
+        *reinterpret_cast<float4*>(d) = make_float4(p[0][pl], p[1][pl], p[2][pl], p[3][pl]);
+      } else {
+        auto bits = [](E x) { return static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&x)); };
+        *reinterpret_cast<uint2*>(d) = make_uint2(bits(p[0][pl]) | (bits(p[1][pl]) << 16),
+                                                  bits(p[2][pl]) | (bits(p[3][pl]) << 16));
+      }
+    }
+  }
+  if (ovf) atomicOr(flags, kFlagRange);
+}
+
 }  // namespace mm

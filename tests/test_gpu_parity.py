@@ -477,3 +477,26 @@ def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sm
     finally:
         for e in engs:
             e.close()
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3"])
+def test_mode_a_reference_literal_shapes(precision):
+    """The shipped pipeline's own network shape (full_pipeline_maMIMO_DNNEst.sh:40,47): input = time-domain LTF
+    (320 samples x 32 symbols = 10240) || P row (32)  ->  1024 -> 1024 -> 234, one packet = 32 x 4 pairs."""
+    nt, nr, len_ltf, d_out, hidden = 32, 4, 10240, 234, (1024, 1024)
+    d_in = len_ltf + nt
+    nets = mm.synth.make_nets(d_in, hidden, d_out)
+    rng = np.random.default_rng(12)
+    sig = (rng.standard_normal((2, nr, len_ltf)) + 1j * rng.standard_normal((2, nr, len_ltf))) * 0.05
+    P = tables.sylvester_hadamard(nt)
+    with mm.Engine(nt, nr, 8, hidden=hidden, d_in=d_in, d_out=d_out, input_mode="time_p", len_ltf=len_ltf,
+                   precision=precision, max_pkts=2) as eng:
+        eng.set_pilots(None, P)
+        eng.load_weights(nets)
+        Yr, Yi = eng.predict_time(sig.real, sig.imag)
+    rows = np.arange(2 * nr * nt)
+    for part, Y, name in ((np.real, Yr, "real"), (np.imag, Yi, "imag")):
+        xsig, xp = postproc.assemble_mode_a(part(sig).astype(np.float32), P.T, rows, nr, nt)   # pickle P = MATLAB P'
+        ref = mlp.forward(np.concatenate([xsig, xp], axis=1), nets[name])
+        assert Y.shape == (2 * nr * nt, d_out)
+        assert rel_l2(ref, Y) <= TOL_DNN, name
