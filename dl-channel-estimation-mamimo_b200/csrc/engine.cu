@@ -98,7 +98,7 @@ struct mamimo_engine {
   float* gather_local[2] = {nullptr, nullptr};                       // this rank's gathered planes (owned)
   float* gather_peer[2][kMaxGatherRanks] = {};                       // every rank's planes as mapped here
   // OFDM front-end (optional)
-  int fft_len = 0, cp_len = 0, sym_offset = 0;
+  int fft_len = 0, cp_len = 0, sym_offset = 0, n_twiddle = 0;
   float2* d_twiddle = nullptr;
   int* d_bins = nullptr;
   float2* d_ydemod = nullptr;   // [max_pkts][n_rx][n_ltf][n_sc] scratch between demod and LS
@@ -494,14 +494,14 @@ mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps
 mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n_pkt, float2* dY, cudaStream_t st) {
   OfdmArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = dx; a.Y = dY; a.twiddle = e->d_twiddle; a.bins = e->d_bins;
+  a.x = dx; a.Y = dY; a.twiddle = e->d_twiddle; a.n_twiddle = e->n_twiddle; a.bins = e->d_bins;
   a.fft_len = e->fft_len; a.cp_len = e->cp_len; a.sym_offset = e->sym_offset;
   a.n_sym = e->cfg.n_ltf; a.n_sc = e->cfg.n_sc; a.x_double = x_double;
   a.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf;
   a.syms_per_cta = std::max(1, std::min(16, 1024 / e->fft_len));   // >= one radix-4 butterfly per thread per stage
   const long long grid = (a.total_syms + a.syms_per_cta - 1) / a.syms_per_cta;
   const int threads = 256;
-  const size_t smem = static_cast<size_t>(a.syms_per_cta) * 2 * e->fft_len * sizeof(float2);
+  const size_t smem = (static_cast<size_t>(a.syms_per_cta) * 2 * e->fft_len + e->n_twiddle) * sizeof(float2);
   if (smem > 48 * 1024)
     CK(e, cudaFuncSetAttribute(ofdm_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
@@ -1167,12 +1167,25 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
     if (carriers[k] < 1 || carriers[k] > fft_len) return fail(e, MAMIMO_ERR_INVALID, "carrier index out of range");
     bins[k] = (carriers[k] - 1 + fft_len / 2) % fft_len;      // undo fftshift: shifted index -> natural FFT bin
   }
-  std::vector<float> tw(static_cast<size_t>(2) * fft_len);    // [fft] complex: exp(-2 pi i m / fft)
+  // per-stage compact twiddle tables (FP64 -> FP32): radix-4 stage ns: w_r[k] = exp(-2 pi i r k / (4 ns)), r = 1..3,
+  // k < ns; then the radix-2 tail stage (log2 fft odd): w[k] = exp(-2 pi i k / (2 ns))
+  std::vector<float> tw;
   const double two_pi = 6.283185307179586476925286766559;
-  for (int k = 0; k < fft_len; ++k) {
-    tw[2 * k] = static_cast<float>(std::cos(two_pi * k / fft_len));
-    tw[2 * k + 1] = static_cast<float>(-std::sin(two_pi * k / fft_len));
-  }
+  int ns = 1;
+  for (; ns * 4 <= fft_len; ns *= 4)
+    for (int r = 1; r <= 3; ++r)
+      for (int k = 0; k < ns; ++k) {
+        const double ang = -two_pi * r * k / (4.0 * ns);
+        tw.push_back(static_cast<float>(std::cos(ang)));
+        tw.push_back(static_cast<float>(std::sin(ang)));
+      }
+  if (ns < fft_len)
+    for (int k = 0; k < ns; ++k) {
+      const double ang = -two_pi * k / (2.0 * ns);
+      tw.push_back(static_cast<float>(std::cos(ang)));
+      tw.push_back(static_cast<float>(std::sin(ang)));
+    }
+  e->n_twiddle = static_cast<int>(tw.size() / 2);
   if (e->d_twiddle) { cudaFree(e->d_twiddle); e->d_twiddle = nullptr; }
   if (e->d_bins) { cudaFree(e->d_bins); e->d_bins = nullptr; }
   CK(e, cudaMalloc(&e->d_twiddle, std::max<size_t>(8, tw.size() * sizeof(float))));

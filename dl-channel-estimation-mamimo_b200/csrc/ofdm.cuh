@@ -18,7 +18,8 @@ namespace mm {
 struct OfdmArgs {
   const void* x;            // complex [n_pkt*n_rx][n_sym*(fft+cp)]  float2 or double2
   float2* Y;                // complex64 [n_pkt*n_rx][n_sym][n_sc]
-  const float2* twiddle;    // [fft]  exp(-2*pi*i*m/fft)
+  const float2* twiddle;    // per-stage compact tables, see kernel: [stage][r=1..3][k<ns] then the radix-2 tail [k<ns]
+  int n_twiddle;            // entries in that table
   const int* bins;          // [n_sc] natural-order FFT bin of each kept carrier
   int fft_len, cp_len, sym_offset, n_sym, n_sc;
   int syms_per_cta;         // symbols transformed side by side in one CTA
@@ -31,17 +32,22 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 }
 
 __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
-  extern __shared__ float2 sm_fft[];                 // [syms_per_cta][2][fft_len]
+  extern __shared__ float2 sm_fft[];                 // [syms_per_cta][2][fft_len] then the twiddle tables
   const int N = a.fft_len;
   const int S = a.syms_per_cta;
   const long long sym0 = static_cast<long long>(blockIdx.x) * S;
   const int n_here = static_cast<int>(min(static_cast<long long>(S), a.total_syms - sym0));
   const int sym_len = N + a.cp_len;
+  const int lgN = 31 - __clz(N);                      // N is a power of two: shifts, not divisions
+  // twiddles: stage ns uses w_r[k] = exp(-2 pi i r k / (4 ns)), k < ns, stored contiguously per (stage, r) so
+  // that consecutive butterflies (consecutive k) read consecutive entries: conflict-free, no scattered gathers
+  float2* tw = sm_fft + static_cast<size_t>(S) * 2 * N;
+  for (int i = threadIdx.x; i < a.n_twiddle; i += blockDim.x) tw[i] = a.twiddle[i];
   // window[i] = x[ix(i)],  ix = [cp, fft+off) ++ [off, cp)   (dataGenerator.py:442).  Symbols of one (pkt,rx)
   // stream are contiguous in x, and streams follow each other, so global symbol g starts at g * sym_len.
   const int first = N + a.sym_offset - a.cp_len;
   for (int idx = threadIdx.x; idx < n_here * N; idx += blockDim.x) {
-    const int s = idx / N, i = idx - s * N;
+    const int s = idx >> lgN, i = idx & (N - 1);
     const int src = (i < first) ? (a.cp_len + i) : (a.sym_offset + (i - first));
     const size_t g = static_cast<size_t>(sym0 + s) * sym_len + src;
     float2 v;
@@ -58,17 +64,20 @@ __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
   int cur = 0;                                        // which ping-pong half holds the data
   const int quarter = N >> 2;
   int ns = 1;
-  for (; ns * 4 <= N; ns <<= 2) {                     // radix-4 stages
-    const int stride = N / (4 * ns);
+  int tw_off = 0;
+  for (; ns * 4 <= N; tw_off += 3 * ns, ns <<= 2) {   // radix-4 stages
+    const float2* w1 = tw + tw_off;
+    const float2* w2 = w1 + ns;
+    const float2* w3 = w2 + ns;
     for (int idx = threadIdx.x; idx < n_here * quarter; idx += blockDim.x) {
-      const int s = idx / quarter, j = idx - s * quarter;
+      const int s = idx >> (lgN - 2), j = idx & (quarter - 1);
       const float2* in = sm_fft + static_cast<size_t>(s) * 2 * N + cur * N;
       float2* out = sm_fft + static_cast<size_t>(s) * 2 * N + (cur ^ 1) * N;
       const int k = j & (ns - 1);
       const float2 v0 = in[j];
-      const float2 v1 = cmulf(in[j + quarter], a.twiddle[k * stride]);
-      const float2 v2 = cmulf(in[j + 2 * quarter], a.twiddle[2 * k * stride]);
-      const float2 v3 = cmulf(in[j + 3 * quarter], a.twiddle[3 * k * stride]);
+      const float2 v1 = cmulf(in[j + quarter], w1[k]);
+      const float2 v2 = cmulf(in[j + 2 * quarter], w2[k]);
+      const float2 v3 = cmulf(in[j + 3 * quarter], w3[k]);
       const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y);
       const float2 t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
       const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
@@ -84,14 +93,14 @@ __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
   }
   if (ns < N) {                                       // one radix-2 stage left (log2 N odd)
     const int half = N >> 1;
-    const int stride = N / (2 * ns);
+    const float2* w1 = tw + tw_off;
     for (int idx = threadIdx.x; idx < n_here * half; idx += blockDim.x) {
-      const int s = idx / half, j = idx - s * half;
+      const int s = idx >> (lgN - 1), j = idx & (half - 1);
       const float2* in = sm_fft + static_cast<size_t>(s) * 2 * N + cur * N;
       float2* out = sm_fft + static_cast<size_t>(s) * 2 * N + (cur ^ 1) * N;
       const int k = j & (ns - 1);
       const float2 u = in[j];
-      const float2 v = cmulf(in[j + half], a.twiddle[k * stride]);
+      const float2 v = cmulf(in[j + half], w1[k]);
       const int d = ((j - k) << 1) + k;
       out[d] = make_float2(u.x + v.x, u.y + v.y);
       out[d + ns] = make_float2(u.x - v.x, u.y - v.y);
@@ -100,9 +109,10 @@ __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
     cur ^= 1;
   }
   // symbols are contiguous in Y too ([stream][sym][k]): global symbol g writes at g * n_sc
-  for (int idx = threadIdx.x; idx < n_here * a.n_sc; idx += blockDim.x) {
-    const int s = idx / a.n_sc, k = idx - s * a.n_sc;
-    a.Y[static_cast<size_t>(sym0 + s) * a.n_sc + k] = sm_fft[static_cast<size_t>(s) * 2 * N + cur * N + a.bins[k]];
+  for (int s = 0; s < n_here; ++s) {
+    const float2* res = sm_fft + static_cast<size_t>(s) * 2 * N + cur * N;
+    float2* out = a.Y + static_cast<size_t>(sym0 + s) * a.n_sc;
+    for (int k = threadIdx.x; k < a.n_sc; k += blockDim.x) out[k] = res[__ldg(a.bins + k)];
   }
 }
 
