@@ -70,6 +70,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
   unsigned long long* d_dbg = nullptr;   // MAMIMO_FC_DEBUG=1: role wait-cycle counters of the pair kernel
   int l2_prefetch = 0;             // measured slower (426 vs 442 TFLOP/s): kept as an experiment knob (MAMIMO_L2_PREFETCH)
   int rows_alloc = 0;           // plane stride (rows) of every activation operand
@@ -262,8 +263,27 @@ mamimo_status launch_ls_t(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   return MAMIMO_OK;
 }
 
+template <int S, int NLTF>
+mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+  const int n_tiles = (a.n_pil + 63) / 64;
+  const long long grid = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
+  const size_t smem = static_cast<size_t>(NLTF) * (64 + 4) * sizeof(float2);
+  {
+    ProfScope ps(e, st, kClsLs);
+    ls_had_split_kernel<S, NLTF><<<static_cast<unsigned>(grid), 64 * (NLTF / 16), smem, st>>>(a);
+  }
+  CK(e, cudaGetLastError());
+  e->stats.kernel_launches++;
+  return MAMIMO_OK;
+}
+
 template <int S>
 mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+  // every reference call site (n_ps = 1, Hadamard P, 32 or 64 antennas): transform split over threads
+  if (e->hadamard && a.n_ps == 1 && e->ls_split) {
+    if (a.n_ltf == 32) return launch_ls_split<S, 32>(e, a, st);
+    if (a.n_ltf == 64) return launch_ls_split<S, 64>(e, a, st);
+  }
 #define LS_CASE(n)                                                    \
   case n:                                                             \
     return e->hadamard ? launch_ls_t<S, n, true>(e, a, st) : launch_ls_t<S, n, false>(e, a, st);
@@ -753,6 +773,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
+  if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_FC_DEBUG")) {
     if (atoi(env) && cudaMalloc(&e->d_dbg, 8 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_dbg, 0, 8 * sizeof(unsigned long long));

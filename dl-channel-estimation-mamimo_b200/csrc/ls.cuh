@@ -62,93 +62,12 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// HAD: P is Sylvester-Hadamard and n_tx == n_ltf == NLTF -> FWHT despread.  Otherwise a dense complex
-// matvec against P (shared memory); NLTF > 0 unrolls it over registers, NLTF == 0 is the any-size
-// (n_ltf <= 64) fallback.
-template <int S, int NLTF, bool HAD>
-__global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
+// Phase 2 of the LS kernels: the CTA sweeps (tx, k) of its tile with k fastest, interpolates between pilots when
+// n_ps > 1 (n_ps == 1 is a pure copy: bit-exact identity) and writes H_ls and the split operand planes.
+template <int S>
+__device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int pitch, int prx, int pil0, int lo) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
-  extern __shared__ float2 sm_ls[];
-  const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
-  const int tile = blockIdx.x % n_tiles;
-  const int prx = blockIdx.x / n_tiles;                 // pkt * n_rx + rx
-  const int pil0 = tile * a.pil_per_tile;
-  // pilots held by this CTA: [lo, hi) = tile pilots plus one halo pilot on each side (interp only)
-  const int lo = (a.n_ps > 1 && pil0 > 0) ? pil0 - 1 : pil0;
-  int hi = min(pil0 + a.pil_per_tile, a.n_pil);
-  if (a.n_ps > 1 && hi < a.n_pil) hi += 1;
-  const int n_hold = hi - lo;
-  const int pitch = a.pil_per_tile + 4;                 // even pitch: rows stay 16-byte aligned for float4 reads
-  float2* sh = sm_ls;                                   // [n_tx][pitch]
-  float2* sP = sm_ls + static_cast<size_t>(a.n_tx) * pitch;   // dense path: [n_tx][n_ltf]
-
-  if constexpr (!HAD) {
-    for (int i = threadIdx.x; i < a.n_tx * a.n_ltf; i += blockDim.x) sP[i] = a.P[i];
-    __syncthreads();
-  }
-
-  // ---- phase 1: despread at pilot tones -------------------------------------------------
-  const size_t y_base = static_cast<size_t>(prx) * a.n_ltf * a.n_sc;
-  for (int t = threadIdx.x; t < n_hold; t += blockDim.x) {
-    const int pil = lo + t;
-    const int k = pil * a.n_ps;
-    const float2 inv = __ldg(a.inv_den + pil);
-    if constexpr (HAD) {
-      // H_NLTF = H_NB (x) H_BLK: 16-point transforms in registers (keeps the kernel at <= 6 CTAs/SM worth
-      // of registers), the outer NB-point stage through this thread's own shared-memory column
-      constexpr int BLK = NLTF < 16 ? NLTF : 16;
-      constexpr int NB = NLTF / BLK;
-#pragma unroll 1
-      for (int b = 0; b < NB; ++b) {      // not unrolled: 16 loads in flight per thread, ~70 registers
-        float2 v[BLK];
-#pragma unroll
-        for (int n = 0; n < BLK; ++n)
-          v[n] = ld_y(a.Y, y_base + static_cast<size_t>(b * BLK + n) * a.n_sc + k, a.y_double);
-        fwht<BLK>(v);
-#pragma unroll
-        for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * pitch + t] = (NB == 1) ? cmul(v[j], inv) : v[j];
-      }
-      if constexpr (NB > 1) {
-#pragma unroll 4
-        for (int j = 0; j < BLK; ++j) {
-          float2 u[NB];
-#pragma unroll
-          for (int b = 0; b < NB; ++b) u[b] = sh[(b * BLK + j) * pitch + t];
-          fwht<NB>(u);
-#pragma unroll
-          for (int b = 0; b < NB; ++b) sh[(b * BLK + j) * pitch + t] = cmul(u[b], inv);
-        }
-      }
-    } else if constexpr (NLTF > 0) {
-      float2 v[NLTF];
-#pragma unroll
-      for (int n = 0; n < NLTF; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
-      for (int j = 0; j < a.n_tx; ++j) {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int n = 0; n < NLTF; ++n) {
-          const float2 p = sP[j * NLTF + n];              // y * conj(p)
-          acc.x += v[n].x * p.x + v[n].y * p.y;
-          acc.y += v[n].y * p.x - v[n].x * p.y;
-        }
-        sh[j * pitch + t] = cmul(acc, inv);
-      }
-    } else {
-      for (int j = 0; j < a.n_tx; ++j) {
-        float2 acc = make_float2(0.f, 0.f);
-        for (int n = 0; n < a.n_ltf; ++n) {
-          const float2 y = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
-          const float2 p = sP[j * a.n_ltf + n];
-          acc.x += y.x * p.x + y.y * p.y;
-          acc.y += y.y * p.x - y.x * p.y;
-        }
-        sh[j * pitch + t] = cmul(acc, inv);
-      }
-    }
-  }
-  __syncthreads();
-
   // ---- phase 2: interpolate + emit ------------------------------------------------------
   const int k0 = pil0 * a.n_ps;
   const int k1 = (pil0 + a.pil_per_tile >= a.n_pil) ? a.n_sc : min(a.n_sc, (pil0 + a.pil_per_tile) * a.n_ps);
@@ -241,6 +160,143 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
     }
   }
   if (ovf) atomicOr(a.flags, kFlagRange);
+}
+
+// HAD: P is Sylvester-Hadamard and n_tx == n_ltf == NLTF -> FWHT despread.  Otherwise a dense complex
+// matvec against P (shared memory); NLTF > 0 unrolls it over registers, NLTF == 0 is the any-size
+// (n_ltf <= 64) fallback.
+template <int S, int NLTF, bool HAD>
+__global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  extern __shared__ float2 sm_ls[];
+  const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
+  const int tile = blockIdx.x % n_tiles;
+  const int prx = blockIdx.x / n_tiles;                 // pkt * n_rx + rx
+  const int pil0 = tile * a.pil_per_tile;
+  // pilots held by this CTA: [lo, hi) = tile pilots plus one halo pilot on each side (interp only)
+  const int lo = (a.n_ps > 1 && pil0 > 0) ? pil0 - 1 : pil0;
+  int hi = min(pil0 + a.pil_per_tile, a.n_pil);
+  if (a.n_ps > 1 && hi < a.n_pil) hi += 1;
+  const int n_hold = hi - lo;
+  const int pitch = a.pil_per_tile + 4;                 // even pitch: rows stay 16-byte aligned for float4 reads
+  float2* sh = sm_ls;                                   // [n_tx][pitch]
+  float2* sP = sm_ls + static_cast<size_t>(a.n_tx) * pitch;   // dense path: [n_tx][n_ltf]
+
+  if constexpr (!HAD) {
+    for (int i = threadIdx.x; i < a.n_tx * a.n_ltf; i += blockDim.x) sP[i] = a.P[i];
+    __syncthreads();
+  }
+
+  // ---- phase 1: despread at pilot tones -------------------------------------------------
+  const size_t y_base = static_cast<size_t>(prx) * a.n_ltf * a.n_sc;
+  for (int t = threadIdx.x; t < n_hold; t += blockDim.x) {
+    const int pil = lo + t;
+    const int k = pil * a.n_ps;
+    const float2 inv = __ldg(a.inv_den + pil);
+    if constexpr (HAD) {
+      // H_NLTF = H_NB (x) H_BLK: 16-point transforms in registers (keeps the kernel at <= 6 CTAs/SM worth
+      // of registers), the outer NB-point stage through this thread's own shared-memory column
+      constexpr int BLK = NLTF < 16 ? NLTF : 16;
+      constexpr int NB = NLTF / BLK;
+#pragma unroll 1
+      for (int b = 0; b < NB; ++b) {      // not unrolled: 16 loads in flight per thread, ~70 registers
+        float2 v[BLK];
+#pragma unroll
+        for (int n = 0; n < BLK; ++n)
+          v[n] = ld_y(a.Y, y_base + static_cast<size_t>(b * BLK + n) * a.n_sc + k, a.y_double);
+        fwht<BLK>(v);
+#pragma unroll
+        for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * pitch + t] = (NB == 1) ? cmul(v[j], inv) : v[j];
+      }
+      if constexpr (NB > 1) {
+#pragma unroll 4
+        for (int j = 0; j < BLK; ++j) {
+          float2 u[NB];
+#pragma unroll
+          for (int b = 0; b < NB; ++b) u[b] = sh[(b * BLK + j) * pitch + t];
+          fwht<NB>(u);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) sh[(b * BLK + j) * pitch + t] = cmul(u[b], inv);
+        }
+      }
+    } else if constexpr (NLTF > 0) {
+      float2 v[NLTF];
+#pragma unroll
+      for (int n = 0; n < NLTF; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
+      for (int j = 0; j < a.n_tx; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NLTF; ++n) {
+          const float2 p = sP[j * NLTF + n];              // y * conj(p)
+          acc.x += v[n].x * p.x + v[n].y * p.y;
+          acc.y += v[n].y * p.x - v[n].x * p.y;
+        }
+        sh[j * pitch + t] = cmul(acc, inv);
+      }
+    } else {
+      for (int j = 0; j < a.n_tx; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int n = 0; n < a.n_ltf; ++n) {
+          const float2 y = ld_y(a.Y, y_base + static_cast<size_t>(n) * a.n_sc + k, a.y_double);
+          const float2 p = sP[j * a.n_ltf + n];
+          acc.x += y.x * p.x + y.y * p.y;
+          acc.y += y.y * p.x - y.x * p.y;
+        }
+        sh[j * pitch + t] = cmul(acc, inv);
+      }
+    }
+  }
+  __syncthreads();
+
+  ls_emit<S>(a, sh, pitch, prx, pil0, lo);
+}
+
+// Hadamard despread with the transform split over threads (n_ps == 1, NLTF = 32 or 64): a CTA owns 64 tones;
+// thread (tone t, block b) pulls 16 symbols, does a 16-point FWHT in registers and parks it in shared memory;
+// after a barrier the NB-point outer stage runs on the thread's share of the rows.  64 * NB threads, ~17 KB
+// (NLTF 32) / 35 KB (NLTF 64) of shared memory and ~50 registers: twice the resident warps of the
+// one-thread-per-tone kernel, and every thread has 16 independent loads in flight.
+template <int S, int NLTF>
+__global__ void __launch_bounds__(64 * (NLTF / 16)) ls_had_split_kernel(const LsArgs a) {
+  constexpr int BLK = 16, NB = NLTF / BLK, T = 64;
+  extern __shared__ float2 sm_ls[];
+  const int n_tiles = (a.n_pil + T - 1) / T;
+  const int tile = blockIdx.x % n_tiles;
+  const int prx = blockIdx.x / n_tiles;
+  const int pil0 = tile * T;
+  const int n_here = min(T, a.n_pil - pil0);
+  const int pitch = T + 4;
+  float2* sh = sm_ls;                                   // [NLTF][pitch]
+  const int t = threadIdx.x & (T - 1);
+  const int b = threadIdx.x >> 6;
+  const size_t y_base = static_cast<size_t>(prx) * a.n_ltf * a.n_sc + pil0 + t;
+  if (t < n_here) {
+    float2 v[BLK];
+#pragma unroll
+    for (int n = 0; n < BLK; ++n) v[n] = ld_y(a.Y, y_base + static_cast<size_t>(b * BLK + n) * a.n_sc, a.y_double);
+    fwht<BLK>(v);
+#pragma unroll
+    for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * pitch + t] = v[j];
+  }
+  __syncthreads();
+  if (t < n_here) {
+    const float2 inv = __ldg(a.inv_den + pil0 + t);
+#pragma unroll
+    for (int jj = 0; jj < BLK / NB; ++jj) {
+      const int j = b + jj * NB;
+      float2 u[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) u[c] = sh[(c * BLK + j) * pitch + t];
+      fwht<NB>(u);
+#pragma unroll
+      for (int c = 0; c < NB; ++c) sh[(c * BLK + j) * pitch + t] = cmul(u[c], inv);
+    }
+  }
+  __syncthreads();
+  LsArgs a2 = a;
+  a2.pil_per_tile = T;
+  ls_emit<S>(a2, sh, pitch, prx, pil0, pil0);
 }
 
 // ---- mode B: caller planes float32 [rows][d_in] -> operand planes (inference.py:29-30) ----
