@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
     """Compile the library if missing or older than its sources.  Returns the .so path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("MAMIMO_NVCC_EXTRA", "").split()      # e.g. -DMAMIMO_FC_DEBUG_COUNTERS
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:

@@ -26,6 +26,14 @@
 
 namespace mm {
 
+// Role wait-cycle counters of the pair kernel are compiled in only with -DMAMIMO_FC_DEBUG_COUNTERS (they cost
+// registers in the 40-register producer/MMA warps); see engine.cu MAMIMO_FC_DEBUG.
+#ifdef MAMIMO_FC_DEBUG_COUNTERS
+#define MM_DBG(a) ((a).dbg != nullptr)
+#else
+#define MM_DBG(a) false
+#endif
+
 struct FcArgs {
   int M;                 // valid rows
   int N;                 // valid output features
@@ -418,7 +426,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         uint32_t phase = 0;
         bool ok = true;
         long long dbg_wait = 0;
-        const long long dbg_t0 = a.dbg ? clock64() : 0;
+        const long long dbg_t0 = MM_DBG(a) ? clock64() : 0;
         for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
           const int m_pair = tile / n_tiles, n_blk = tile % n_tiles;
           const int row0 = (m_pair * 2 + static_cast<int>(cta_rank)) * kFcBlockM;        // this CTA's activation rows
@@ -429,9 +437,9 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const int next_row0 = next_tile < total_tiles
                                     ? ((next_tile / n_tiles) * 2 + static_cast<int>(cta_rank)) * kFcBlockM : -1;
           for (int kb = 0; kb < a.num_k_blocks; ++kb) {
-            const long long t_w = a.dbg ? clock64() : 0;
+            const long long t_w = MM_DBG(a) ? clock64() : 0;
             if (!mbar_wait(empty_bar + stage, phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
-            if (a.dbg) dbg_wait += clock64() - t_w;
+            if (MM_DBG(a)) dbg_wait += clock64() - t_w;
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             if (next_row0 >= 0 && a.l2_prefetch) {
 #pragma unroll
@@ -450,7 +458,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        if (a.dbg && leader) {
+        if (MM_DBG(a) && leader) {
           atomicAdd(a.dbg + 0, static_cast<unsigned long long>(dbg_wait));              // producer: waiting for a free stage
           atomicAdd(a.dbg + 1, static_cast<unsigned long long>(clock64() - dbg_t0));    // producer: total
         }
@@ -464,21 +472,21 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         bool ok = true;
         uint32_t unit = 0;
         long long w_tempty = 0, w_full = 0;
-        const long long dbg_t0 = a.dbg ? clock64() : 0;
+        const long long dbg_t0 = MM_DBG(a) ? clock64() : 0;
         for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
           for (int c = 0; c < n_chunks && ok; ++c, ++unit) {
             const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
-            const long long t_e = a.dbg ? clock64() : 0;
+            const long long t_e = MM_DBG(a) ? clock64() : 0;
             if (!mbar_wait(tempty_bar + acc, acc_phase ^ 1, cta_abort, a.flags)) { ok = false; break; }
-            if (a.dbg) w_tempty += clock64() - t_e;
+            if (MM_DBG(a)) w_tempty += clock64() - t_e;
             tc_fence_after_sync();
             const uint32_t tmem_d = tmem_base + acc * BN;
             const int kb_end = min(a.num_k_blocks, (c + 1) * kbc);
             uint32_t fresh = 1;
             for (int kb = c * kbc; kb < kb_end; ++kb) {
-              const long long t_f = a.dbg ? clock64() : 0;
+              const long long t_f = MM_DBG(a) ? clock64() : 0;
               if (!mbar_wait(full_bar + stage, phase, cta_abort, a.flags)) { ok = false; break; }
-              if (a.dbg) w_full += clock64() - t_f;
+              if (MM_DBG(a)) w_full += clock64() - t_f;
               tc_fence_after_sync();
               const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
               const uint32_t sb = sa + kPlanes * Cfg::kABytes;
@@ -498,7 +506,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (ok) umma_commit_pair(tfull_bar + acc, 3);   // both CTAs' epilogues may drain
           }
         }
-        if (a.dbg) {
+        if (MM_DBG(a)) {
           atomicAdd(a.dbg + 2, static_cast<unsigned long long>(w_tempty));               // MMA: waiting for a drained TMEM buffer
           atomicAdd(a.dbg + 3, static_cast<unsigned long long>(w_full));                 // MMA: waiting for operands
           atomicAdd(a.dbg + 4, static_cast<unsigned long long>(clock64() - dbg_t0));     // MMA: total
