@@ -518,10 +518,10 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
   a.fft_len = e->fft_len; a.cp_len = e->cp_len; a.sym_offset = e->sym_offset;
   a.n_sym = e->cfg.n_ltf; a.n_sc = e->cfg.n_sc; a.x_double = x_double;
   a.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf;
-  a.syms_per_cta = std::max(1, std::min(32, 2048 / e->fft_len));   // one radix-16 butterfly per thread per pass
+  a.syms_per_cta = std::max(1, std::min(16, 1024 / e->fft_len));   // >= one radix-4 butterfly per thread per stage
   const long long grid = (a.total_syms + a.syms_per_cta - 1) / a.syms_per_cta;
-  const int threads = kOfdmThreads;
-  const size_t smem = (static_cast<size_t>(a.syms_per_cta) * 2 * pad16(e->fft_len) + e->n_twiddle) * sizeof(float2);
+  const int threads = 256;
+  const size_t smem = (static_cast<size_t>(a.syms_per_cta) * 2 * e->fft_len + e->n_twiddle) * sizeof(float2);
   if (smem > 48 * 1024)
     CK(e, cudaFuncSetAttribute(ofdm_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
@@ -1188,22 +1188,24 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
     if (carriers[k] < 1 || carriers[k] > fft_len) return fail(e, MAMIMO_ERR_INVALID, "carrier index out of range");
     bins[k] = (carriers[k] - 1 + fft_len / 2) % fft_len;      // undo fftshift: shifted index -> natural FFT bin
   }
-  // per-pass compact twiddle tables (FP64 -> FP32), in the order ofdm_demod_kernel runs its passes: radix-16 while
-  // 16 ns <= N, then one radix-4 if 4 ns <= N, then radix-2; pass (R, ns): w[r-1][k] = exp(-2 pi i r k / (R ns))
+  // per-stage compact twiddle tables (FP64 -> FP32): radix-4 stage ns: w_r[k] = exp(-2 pi i r k / (4 ns)), r = 1..3,
+  // k < ns; then the radix-2 tail stage (log2 fft odd): w[k] = exp(-2 pi i k / (2 ns))
   std::vector<float> tw;
   const double two_pi = 6.283185307179586476925286766559;
-  auto emit = [&](int R, int ns_) {
-    for (int r = 1; r < R; ++r)
-      for (int k = 0; k < ns_; ++k) {
-        const double ang = -two_pi * r * k / (static_cast<double>(R) * ns_);
+  int ns = 1;
+  for (; ns * 4 <= fft_len; ns *= 4)
+    for (int r = 1; r <= 3; ++r)
+      for (int k = 0; k < ns; ++k) {
+        const double ang = -two_pi * r * k / (4.0 * ns);
         tw.push_back(static_cast<float>(std::cos(ang)));
         tw.push_back(static_cast<float>(std::sin(ang)));
       }
-  };
-  int ns = 1;
-  for (; ns * 16 <= fft_len; ns *= 16) emit(16, ns);
-  if (ns * 4 <= fft_len) { emit(4, ns); ns *= 4; }
-  for (; ns < fft_len; ns *= 2) emit(2, ns);
+  if (ns < fft_len)
+    for (int k = 0; k < ns; ++k) {
+      const double ang = -two_pi * k / (2.0 * ns);
+      tw.push_back(static_cast<float>(std::cos(ang)));
+      tw.push_back(static_cast<float>(std::sin(ang)));
+    }
   e->n_twiddle = static_cast<int>(tw.size() / 2);
   if (e->d_twiddle) { cudaFree(e->d_twiddle); e->d_twiddle = nullptr; }
   if (e->d_bins) { cudaFree(e->d_bins); e->d_bins = nullptr; }
