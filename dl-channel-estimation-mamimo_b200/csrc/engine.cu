@@ -101,6 +101,8 @@ struct mamimo_engine {
   // OFDM front-end (optional)
   int fft_len = 0, cp_len = 0, sym_offset = 0, n_twiddle = 0;
   float2* d_twiddle = nullptr;
+  float2* d_tw256 = nullptr;    // FFT-256 specialisation: pass-2 twiddles [15][16]
+  int* d_kmap = nullptr;        // [fft_len] FFT bin -> output column (-1 = dropped)
   int* d_bins = nullptr;
   float2* d_ydemod = nullptr;   // [max_pkts][n_rx][n_ltf][n_sc] scratch between demod and LS
   uint32_t* d_flags = nullptr;
@@ -512,6 +514,21 @@ mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps
 }
 
 mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n_pkt, float2* dY, cudaStream_t st) {
+  if (e->fft_len == 256 && e->d_tw256 && getenv("MAMIMO_OFDM_GENERIC") == nullptr) {
+    Ofdm256Args b;
+    memset(&b, 0, sizeof(b));
+    b.x = dx; b.Y = dY; b.tw2 = e->d_tw256; b.kmap = e->d_kmap;
+    b.cp_len = e->cp_len; b.sym_offset = e->sym_offset; b.n_sc = e->cfg.n_sc;
+    b.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf; b.x_double = x_double;
+    const long long grid = (b.total_syms + 7) / 8;
+    {
+      ProfScope ps(e, st, kClsStage);
+      ofdm256_kernel<<<static_cast<unsigned>(grid), 128, 0, st>>>(b);
+    }
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return MAMIMO_OK;
+  }
   OfdmArgs a;
   memset(&a, 0, sizeof(a));
   a.x = dx; a.Y = dY; a.twiddle = e->d_twiddle; a.n_twiddle = e->n_twiddle; a.bins = e->d_bins;
@@ -857,7 +874,7 @@ void mamimo_destroy(mamimo_engine* e) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_kmap); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -1215,6 +1232,25 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
   CK(e, cudaMemcpy(e->d_bins, bins.data(), bins.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (!e->d_ydemod)
     CK(e, cudaMalloc(&e->d_ydemod, static_cast<size_t>(e->max_pkts) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * sizeof(float2)));
+  {
+    std::vector<int> kmap(fft_len, -1);
+    for (int k = 0; k < e->cfg.n_sc; ++k) kmap[bins[k]] = k;
+    if (e->d_kmap) { cudaFree(e->d_kmap); e->d_kmap = nullptr; }
+    CK(e, cudaMalloc(&e->d_kmap, kmap.size() * sizeof(int)));
+    CK(e, cudaMemcpy(e->d_kmap, kmap.data(), kmap.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (e->d_tw256) { cudaFree(e->d_tw256); e->d_tw256 = nullptr; }
+    if (fft_len == 256) {
+      std::vector<float> t2(2 * 15 * 16);
+      for (int r = 1; r < 16; ++r)
+        for (int k = 0; k < 16; ++k) {
+          const double ang = -6.283185307179586476925286766559 * r * k / 256.0;
+          t2[2 * ((r - 1) * 16 + k)] = static_cast<float>(std::cos(ang));
+          t2[2 * ((r - 1) * 16 + k) + 1] = static_cast<float>(std::sin(ang));
+        }
+      CK(e, cudaMalloc(&e->d_tw256, t2.size() * sizeof(float)));
+      CK(e, cudaMemcpy(e->d_tw256, t2.data(), t2.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
   e->fft_len = fft_len; e->cp_len = cp_len; e->sym_offset = sym_offset;
   return MAMIMO_OK;
 }

@@ -116,4 +116,107 @@ __global__ void __launch_bounds__(256) ofdm_demod_kernel(const OfdmArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FFT-256 specialisation (the reference numerology, generate_maMIMO_LTF.m:96-102): 256 = 16 x 16, so the whole
+// transform is two radix-16 passes with the 16-point DFT in registers.  Pass 1 reads the window straight from
+// global memory, pass 2 writes the kept carriers straight to global memory: one shared-memory buffer, one
+// barrier, 16 B of shared-memory traffic per point (the generic kernel moves ~110 B).  16 threads per symbol,
+// 8 symbols per 128-thread CTA, 17 KB of shared memory (rows padded 1-in-16: conflict-free both ways).
+__host__ __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)
+
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  const float2 t0 = caddf(v0, v2), t1 = csubf(v0, v2), t2 = caddf(v1, v3), t3 = cmul_negi(csubf(v1, v3));
+  v0 = caddf(t0, t2);
+  v1 = caddf(t1, t3);
+  v2 = csubf(t0, t2);
+  v3 = csubf(t1, t3);
+}
+
+// forward DFT-16 in registers, natural order in and out (4 x 4 Cooley-Tukey):
+//   X[k1 + 4 k2] = sum_n2 W16^(n2 k1) W4^(n2 k2) ( sum_n1 x[4 n1 + n2] W4^(n1 k1) )
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508978f, h = 0.70710678118654752f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);   // v[4 k1 + n2] = inner[n2][k1]
+  v[4 + 1] = cmulf(v[4 + 1], make_float2(c1, -s1));    // W16^(n2 k1)
+  v[4 + 2] = cmulf(v[4 + 2], make_float2(h, -h));
+  v[4 + 3] = cmulf(v[4 + 3], make_float2(s1, -c1));
+  v[8 + 1] = cmulf(v[8 + 1], make_float2(h, -h));
+  v[8 + 2] = cmul_negi(v[8 + 2]);
+  v[8 + 3] = cmulf(v[8 + 3], make_float2(-h, -h));
+  v[12 + 1] = cmulf(v[12 + 1], make_float2(s1, -c1));
+  v[12 + 2] = cmulf(v[12 + 2], make_float2(-h, -h));
+  v[12 + 3] = cmulf(v[12 + 3], make_float2(-c1, s1));
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // v[4 k1 + k2]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)           // X[k1 + 4 k2] sits in v[4 k1 + k2]: transpose the 4 x 4 register tile
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j) {
+      const float2 t = v[4 * i + j];
+      v[4 * i + j] = v[4 * j + i];
+      v[4 * j + i] = t;
+    }
+}
+
+struct Ofdm256Args {
+  const void* x;
+  float2* Y;
+  const float2* tw2;        // [15][16]  exp(-2 pi i r k / 256), r = 1..15, k < 16 (pass-2 twiddles)
+  const int* kmap;          // [256] natural FFT bin -> output column, or -1 when the carrier is dropped
+  int cp_len, sym_offset, n_sc;
+  long long total_syms;
+  int x_double;
+};
+
+__global__ void __launch_bounds__(128) ofdm256_kernel(const Ofdm256Args a) {
+  constexpr int N = 256, SYMS = 8;
+  __shared__ float2 buf[SYMS][N + N / 16];
+  __shared__ float2 tw[15 * 16];
+  __shared__ int kmap[N];
+  for (int i = threadIdx.x; i < 15 * 16; i += blockDim.x) tw[i] = a.tw2[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) kmap[i] = a.kmap[i];
+  const int s = threadIdx.x >> 4, j = threadIdx.x & 15;
+  const long long g = static_cast<long long>(blockIdx.x) * SYMS + s;
+  const bool live = g < a.total_syms;
+  float2 v[16];
+  if (live) {
+    // window[i] = x[ix(i)], ix = [cp, 256+off) ++ [off, cp)   (dataGenerator.py:442); pass 1 takes i = j + 16 r
+    const int first = N + a.sym_offset - a.cp_len;
+    const size_t base = static_cast<size_t>(g) * (N + a.cp_len);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int i = j + 16 * r;
+      const int src = (i < first) ? (a.cp_len + i) : (a.sym_offset + (i - first));
+      if (a.x_double) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(a.x) + base + src);
+        v[r] = make_float2(static_cast<float>(d.x), static_cast<float>(d.y));
+      } else {
+        v[r] = __ldg(reinterpret_cast<const float2*>(a.x) + base + src);
+      }
+    }
+    dft16(v);                                            // pass 1: ns = 1, no twiddles, output index 16 j + r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s][17 * j + r] = v[r];   // pad16(16 j + r) = 17 j + r
+  }
+  __syncthreads();
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[s][pad16(j + 16 * r)];   // pass 2: ns = 16, k = j
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmulf(v[r], tw[(r - 1) * 16 + j]);
+    dft16(v);                                            // output bin j + 16 r
+    float2* out = a.Y + static_cast<size_t>(g) * a.n_sc;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int k = kmap[j + 16 * r];
+      if (k >= 0) out[k] = v[r];
+    }
+  }
+}
+
 }  // namespace mm
