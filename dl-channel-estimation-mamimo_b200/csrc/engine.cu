@@ -70,6 +70,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  int ls_tile = 64;             // tones per CTA of the split LS kernel (MAMIMO_LS_TILE=128: experiment)
   bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
   unsigned long long* d_dbg = nullptr;   // MAMIMO_FC_DEBUG=1: role wait-cycle counters of the pair kernel
   int l2_prefetch = 0;             // measured slower (426 vs 442 TFLOP/s): kept as an experiment knob (MAMIMO_L2_PREFETCH)
@@ -101,7 +102,8 @@ struct mamimo_engine {
   // OFDM front-end (optional)
   int fft_len = 0, cp_len = 0, sym_offset = 0, n_twiddle = 0;
   float2* d_twiddle = nullptr;
-  float2* d_tw256 = nullptr;    // FFT-256 specialisation: pass-2 twiddles [15][16]
+  float2* d_tw256 = nullptr;    // register-FFT kernels (256..4096): pass-2 twiddles [15][16]
+  float2* d_tw3 = nullptr;      // 512..4096: pass-3 twiddles [fft_len/256 - 1][256]
   int* d_kmap = nullptr;        // [fft_len] FFT bin -> output column (-1 = dropped)
   int* d_bins = nullptr;
   float2* d_ydemod = nullptr;   // [max_pkts][n_rx][n_ltf][n_sc] scratch between demod and LS
@@ -265,14 +267,14 @@ mamimo_status launch_ls_t(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   return MAMIMO_OK;
 }
 
-template <int S, int NLTF>
+template <int S, int NLTF, int T>
 mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
-  const int n_tiles = (a.n_pil + 63) / 64;
+  const int n_tiles = (a.n_pil + T - 1) / T;
   const long long grid = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
-  const size_t smem = static_cast<size_t>(NLTF) * (64 + 4) * sizeof(float2);
+  const size_t smem = static_cast<size_t>(NLTF) * (T + 4) * sizeof(float2);
   {
     ProfScope ps(e, st, kClsLs);
-    ls_had_split_kernel<S, NLTF><<<static_cast<unsigned>(grid), 64 * (NLTF / 16), smem, st>>>(a);
+    ls_had_split_kernel<S, NLTF, T><<<static_cast<unsigned>(grid), T * (NLTF / 16), smem, st>>>(a);
   }
   CK(e, cudaGetLastError());
   e->stats.kernel_launches++;
@@ -283,8 +285,8 @@ template <int S>
 mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   // every reference call site (n_ps = 1, Hadamard P, 32 or 64 antennas): transform split over threads
   if (e->hadamard && a.n_ps == 1 && e->ls_split) {
-    if (a.n_ltf == 32) return launch_ls_split<S, 32>(e, a, st);
-    if (a.n_ltf == 64) return launch_ls_split<S, 64>(e, a, st);
+    if (a.n_ltf == 32) return e->ls_tile == 128 ? launch_ls_split<S, 32, 128>(e, a, st) : launch_ls_split<S, 32, 64>(e, a, st);
+    if (a.n_ltf == 64) return launch_ls_split<S, 64, 64>(e, a, st);
   }
 #define LS_CASE(n)                                                    \
   case n:                                                             \
@@ -524,6 +526,27 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
     {
       ProfScope ps(e, st, kClsStage);
       ofdm256_kernel<<<static_cast<unsigned>(grid), 128, 0, st>>>(b);
+    }
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return MAMIMO_OK;
+  }
+  if (e->fft_len >= 512 && e->fft_len <= 4096 && e->d_tw256 && e->d_tw3 && getenv("MAMIMO_OFDM_GENERIC") == nullptr) {
+    OfdmR16Args b;
+    memset(&b, 0, sizeof(b));
+    b.x = dx; b.Y = dY; b.tw2 = e->d_tw256; b.tw3 = e->d_tw3; b.kmap = e->d_kmap;
+    b.cp_len = e->cp_len; b.sym_offset = e->sym_offset; b.n_sc = e->cfg.n_sc;
+    b.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf; b.x_double = x_double;
+    const int syms = 4096 / e->fft_len;
+    const unsigned grid = static_cast<unsigned>((b.total_syms + syms - 1) / syms);
+    {
+      ProfScope ps(e, st, kClsStage);
+      switch (e->fft_len) {
+        case 512: ofdm_r16_kernel<9><<<grid, 256, 0, st>>>(b); break;
+        case 1024: ofdm_r16_kernel<10><<<grid, 256, 0, st>>>(b); break;
+        case 2048: ofdm_r16_kernel<11><<<grid, 256, 0, st>>>(b); break;
+        default: ofdm_r16_kernel<12><<<grid, 256, 0, st>>>(b); break;
+      }
     }
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
@@ -791,6 +814,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;
   if (const char* env = getenv("MAMIMO_FC_DEBUG")) {
     if (atoi(env) && cudaMalloc(&e->d_dbg, 8 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_dbg, 0, 8 * sizeof(unsigned long long));
@@ -874,7 +898,7 @@ void mamimo_destroy(mamimo_engine* e) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_kmap); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -1239,7 +1263,20 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
     CK(e, cudaMalloc(&e->d_kmap, kmap.size() * sizeof(int)));
     CK(e, cudaMemcpy(e->d_kmap, kmap.data(), kmap.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (e->d_tw256) { cudaFree(e->d_tw256); e->d_tw256 = nullptr; }
-    if (fft_len == 256) {
+    if (e->d_tw3) { cudaFree(e->d_tw3); e->d_tw3 = nullptr; }
+    if (fft_len >= 512) {
+      const int r3 = fft_len / 256;
+      std::vector<float> t3(static_cast<size_t>(2) * (r3 - 1) * 256);
+      for (int r = 1; r < r3; ++r)
+        for (int k = 0; k < 256; ++k) {
+          const double ang = -6.283185307179586476925286766559 * r * k / fft_len;
+          t3[2 * ((r - 1) * 256 + k)] = static_cast<float>(std::cos(ang));
+          t3[2 * ((r - 1) * 256 + k) + 1] = static_cast<float>(std::sin(ang));
+        }
+      CK(e, cudaMalloc(&e->d_tw3, t3.size() * sizeof(float)));
+      CK(e, cudaMemcpy(e->d_tw3, t3.data(), t3.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (fft_len >= 256) {
       std::vector<float> t2(2 * 15 * 16);
       for (int r = 1; r < 16; ++r)
         for (int k = 0; k < 16; ++k) {

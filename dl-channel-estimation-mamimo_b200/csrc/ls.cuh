@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
 // after a barrier the NB-point outer stage runs on the thread's share of the rows.  64 * NB threads, ~17 KB
 // (NLTF 32) / 35 KB (NLTF 64) of shared memory and ~50 registers: twice the resident warps of the
 // one-thread-per-tone kernel, and every thread has 16 independent loads in flight.
-template <int S, int NLTF>
-__global__ void __launch_bounds__(64 * (NLTF / 16)) ls_had_split_kernel(const LsArgs a) {
-  constexpr int BLK = 16, NB = NLTF / BLK, T = 64;
+template <int S, int NLTF, int T = 64>
+__global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsArgs a) {
+  constexpr int BLK = 16, NB = NLTF / BLK;
   extern __shared__ float2 sm_ls[];
   const int n_tiles = (a.n_pil + T - 1) / T;
   const int tile = blockIdx.x % n_tiles;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_had_split_kernel(const Ls
   const int pitch = T + 4;
   float2* sh = sm_ls;                                   // [NLTF][pitch]
   const int t = threadIdx.x & (T - 1);
-  const int b = threadIdx.x >> 6;
+  const int b = threadIdx.x / T;
   const size_t y_base = static_cast<size_t>(prx) * a.n_ltf * a.n_sc + pil0 + t;
   if (t < n_here) {
     float2 v[BLK];

@@ -219,4 +219,120 @@ __global__ void __launch_bounds__(128) ofdm256_kernel(const Ofdm256Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FFT-512 / 1024 / 2048 / 4096 (the BASELINE.json numerologies): N = 16 x 16 x R3 with R3 = N / 256 in {2,4,8,16}.
+// Three register passes (radix 16, radix 16, radix R3), 16 points per thread in every pass, N/16 threads per
+// symbol and 4096/N symbols per 256-thread CTA.  Pass 1 reads the window straight from global memory, pass 3
+// writes the kept carriers straight to global memory; the two exchanges in between go through ONE padded
+// shared-memory buffer (conflict-free both ways), i.e. 32 B of shared-memory traffic per point where the generic
+// radix-4 Stockham kernel moves 16 B per point per stage (80-96 B) plus its twiddle gathers.
+template <int R>
+__device__ __forceinline__ void dft_small(float2 (&v)[R]);
+
+template <>
+__device__ __forceinline__ void dft_small<2>(float2 (&v)[2]) {
+  const float2 a = v[0], b = v[1];
+  v[0] = caddf(a, b);
+  v[1] = csubf(a, b);
+}
+template <>
+__device__ __forceinline__ void dft_small<4>(float2 (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+// 8 = 4 x 2:  X[k1 + 4 k2] = sum_n2 W8^(n2 k1) (-1)^(n2 k2) ( sum_n1 x[2 n1 + n2] W4^(n1 k1) )
+template <>
+__device__ __forceinline__ void dft_small<8>(float2 (&v)[8]) {
+  constexpr float h = 0.70710678118654752f;
+  dft4(v[0], v[2], v[4], v[6]);
+  dft4(v[1], v[3], v[5], v[7]);
+  v[3] = cmulf(v[3], make_float2(h, -h));
+  v[5] = cmul_negi(v[5]);
+  v[7] = cmulf(v[7], make_float2(-h, -h));
+  const float2 x0 = caddf(v[0], v[1]), x4 = csubf(v[0], v[1]);
+  const float2 x1 = caddf(v[2], v[3]), x5 = csubf(v[2], v[3]);
+  const float2 x2 = caddf(v[4], v[5]), x6 = csubf(v[4], v[5]);
+  const float2 x3 = caddf(v[6], v[7]), x7 = csubf(v[6], v[7]);
+  v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+}
+template <>
+__device__ __forceinline__ void dft_small<16>(float2 (&v)[16]) { dft16(v); }
+
+struct OfdmR16Args {
+  const void* x;
+  float2* Y;
+  const float2* tw2;        // [15][16]      exp(-2 pi i r k / 256),  r = 1..15,   k < 16   (pass 2)
+  const float2* tw3;        // [R3-1][256]   exp(-2 pi i r k / N),    r = 1..R3-1, k < 256  (pass 3)
+  const int* kmap;          // [N] natural FFT bin -> output column, or -1 when the carrier is dropped
+  int cp_len, sym_offset, n_sc;
+  long long total_syms;
+  int x_double;
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256) ofdm_r16_kernel(const OfdmR16Args a) {
+  constexpr int N = 1 << LOG2N;
+  constexpr int T = N / 16;            // threads per symbol
+  constexpr int SYMS = 256 / T;        // symbols per CTA == radix-R3 butterflies per thread in pass 3
+  constexpr int R3 = N / 256;
+  static_assert(LOG2N >= 9 && LOG2N <= 12, "three-pass kernel covers 512..4096");
+  __shared__ float2 buf[SYMS][N + N / 16];
+  __shared__ float2 tw[15 * 16];
+  for (int i = threadIdx.x; i < 15 * 16; i += blockDim.x) tw[i] = a.tw2[i];
+  const int s = threadIdx.x / T, j = threadIdx.x % T;
+  const long long g = static_cast<long long>(blockIdx.x) * SYMS + s;
+  const bool live = g < a.total_syms;
+  float2 v[16];
+  if (live) {
+    // window[i] = x[ix(i)], ix = [cp, N+off) ++ [off, cp)   (dataGenerator.py:442); pass 1 takes i = j + T r
+    const int first = N + a.sym_offset - a.cp_len;
+    const size_t base = static_cast<size_t>(g) * (N + a.cp_len);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int i = j + T * r;
+      const int src = (i < first) ? (a.cp_len + i) : (a.sym_offset + (i - first));
+      if (a.x_double) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(a.x) + base + src);
+        v[r] = make_float2(static_cast<float>(d.x), static_cast<float>(d.y));
+      } else {
+        v[r] = __ldg(reinterpret_cast<const float2*>(a.x) + base + src);
+      }
+    }
+    dft16(v);                                            // pass 1: ns = 1, no twiddles, output index 16 j + r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s][17 * j + r] = v[r];   // pad16(16 j + r) = 17 j + r
+  }
+  __syncthreads();
+  const int k = j & 15;
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[s][pad16(j + T * r)];   // pass 2: ns = 16, k = j mod 16
+  }
+  __syncthreads();                                       // every thread holds its inputs: the buffer may be overwritten
+  if (live) {
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmulf(v[r], tw[(r - 1) * 16 + k]);
+    dft16(v);                                            // output index (j - k) 16 + k + 16 r
+    const int o = (j - k) * 16 + k;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s][pad16(o + 16 * r)] = v[r];
+  }
+  __syncthreads();
+  if (live) {
+    float2* out = a.Y + static_cast<size_t>(g) * a.n_sc;
+#pragma unroll
+    for (int b = 0; b < SYMS; ++b) {                     // pass 3: ns = 256, butterfly jj = j + T b, k = jj
+      const int jj = j + T * b;
+      float2 w[R3];
+#pragma unroll
+      for (int r = 0; r < R3; ++r) w[r] = buf[s][pad16(jj + 256 * r)];
+#pragma unroll
+      for (int r = 1; r < R3; ++r) w[r] = cmulf(w[r], __ldg(a.tw3 + (r - 1) * 256 + jj));
+      dft_small<R3>(w);                                  // output bin jj + 256 r
+#pragma unroll
+      for (int r = 0; r < R3; ++r) {
+        const int col = __ldg(a.kmap + jj + 256 * r);
+        if (col >= 0) out[col] = w[r];
+      }
+    }
+  }
+}
+
 }  // namespace mm

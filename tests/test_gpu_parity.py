@@ -385,7 +385,9 @@ def test_staged_estimate_matches_full_call():
 # ------------------------------------------------------------------------------ OFDM front-end
 @pytest.mark.parametrize("fft_len,cp,so,nt,nr,ctype", [(256, 64, 64, 32, 4, np.complex64), (256, 64, 64, 8, 2, np.complex128),
                                                        (64, 16, 5, 4, 2, np.complex64), (1024, 256, 256, 4, 1, np.complex64),
-                                                       (2048, 512, 100, 2, 2, np.complex64)])
+                                                       (2048, 512, 100, 2, 2, np.complex64),
+                                                       (512, 128, 0, 3, 2, np.complex64), (4096, 1024, 1024, 3, 1, np.complex64),
+                                                       (1024, 72, 40, 5, 3, np.complex128), (128, 32, 32, 4, 2, np.complex64)])
 def test_ofdm_demod_parity(fft_len, cp, so, nt, nr, ctype):
     from oracle import ofdm
     rng = np.random.default_rng(fft_len)
