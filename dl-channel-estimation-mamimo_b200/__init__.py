@@ -11,7 +11,7 @@ The directory name contains hyphens, so import it through the root-level shim:
 from . import build, synth, sharding, pipeline  # noqa: F401
 from ._capi import MamimoError, PRECISIONS, INPUT_MODES  # noqa: F401
 from .engine import (Engine, CSIPredictor, helperMIMOChannelEstimate, vht_ltf256, carriers_locations,  # noqa: F401
-                     default_p, pair_row, pinned_empty)
+                     default_p, pair_row, pinned_empty, tau_rms)
 
 __all__ = ["Engine", "CSIPredictor", "helperMIMOChannelEstimate", "vht_ltf256", "carriers_locations",
-           "default_p", "pair_row", "pinned_empty", "MamimoError", "synth", "build", "sharding", "pipeline"]
+           "default_p", "pair_row", "pinned_empty", "tau_rms", "MamimoError", "synth", "build", "sharding", "pipeline"]

@@ -40,7 +40,8 @@ class Stats(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("ls_ms", C.c_double), ("fc_ms", C.c_double), ("stage_ms", C.c_double),
-                ("ls_launches", C.c_uint64), ("fc_launches", C.c_uint64), ("stage_launches", C.c_uint64)]
+                ("ls_launches", C.c_uint64), ("fc_launches", C.c_uint64), ("stage_launches", C.c_uint64),
+                ("lmmse_ms", C.c_double), ("lmmse_launches", C.c_uint64)]
 
 
 # every symbol include/mamimo.h declares (tests/test_capi_symbols.py checks the header against this)
@@ -51,7 +52,7 @@ SYMBOLS = [
     "mamimo_ls_estimate", "mamimo_estimate", "mamimo_estimate_stages", "mamimo_predict_planes", "mamimo_predict_time",
     "mamimo_synchronize", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end",
-    "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time",
+    "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time", "mamimo_lmmse", "mamimo_tau_rms",
     "mamimo_gather_create", "mamimo_gather_connect", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
 ]
 
@@ -90,6 +91,8 @@ def _load():
         "mamimo_set_ofdm": (i32, [vp, i32, i32, i32, C.POINTER(i32)]),
         "mamimo_ofdm_demod": (i32, [vp, vp, i32, i64, vp, i32, vp]),
         "mamimo_estimate_time": (i32, [vp, vp, i32, i64, vp, vp, vp, i32, vp]),
+        "mamimo_lmmse": (i32, [vp, vp, i32, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, i32, i32, vp]),
+        "mamimo_tau_rms": (C.c_double, [C.POINTER(C.c_double), i32, i32]),
         "mamimo_gather_create": (i32, [vp, i32, i32, i64, C.POINTER(vp), C.POINTER(vp)]),
         "mamimo_gather_connect": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "mamimo_ipc_export": (i32, [vp, C.c_char_p]),

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmamimo_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["fc.cuh", "ls.cuh", "ofdm.cuh", "ptx.cuh", "schemes.cuh", "tables.h", os.path.join("..", "..", "include", "mamimo.h")]
+HEADERS = ["fc.cuh", "ls.cuh", "lmmse.cuh", "ofdm.cuh", "ptx.cuh", "schemes.cuh", "tables.h", os.path.join("..", "..", "include", "mamimo.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

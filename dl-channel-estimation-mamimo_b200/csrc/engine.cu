@@ -14,6 +14,7 @@
 
 #include "../../include/mamimo.h"
 #include "fc.cuh"
+#include "lmmse.cuh"
 #include "ls.cuh"
 #include "ofdm.cuh"
 #include "tables.h"
@@ -123,6 +124,14 @@ struct mamimo_engine {
   size_t st_h_bytes = 0;
   void* st_hls[2] = {nullptr, nullptr};
   size_t st_hls_bytes = 0;
+  // LMMSE smoother workspace (lazy)
+  double2* lm_M = nullptr;       // [lm_slabs][R][n_pad]
+  double2* lm_Dinv = nullptr;    // [lm_slabs][nb][32][32]
+  double2* lm_par = nullptr;     // [lm_slabs] (c, 1/snr)
+  void* lm_in = nullptr;         // host-buffer staging of H_ls / H_mmse chunks
+  void* lm_out = nullptr;
+  int lm_slabs = 0;
+  size_t lm_io_bytes = 0;
   mamimo_stats stats;
   // optional per-kernel-class device timing (mamimo_profile_begin/end)
   struct ProfRec { cudaEvent_t a, b; int cls; };
@@ -145,7 +154,7 @@ mamimo_status fail_cuda(mamimo_engine* e, cudaError_t ce, const char* what) {
     if (ce_ != cudaSuccess) return fail_cuda(e, ce_, #call); \
   } while (0)
 
-enum { kClsLs = 0, kClsFc = 1, kClsStage = 2 };   // the OFDM demod kernel is booked under kClsStage
+enum { kClsLs = 0, kClsFc = 1, kClsStage = 2, kClsLmmse = 3 };   // the OFDM demod kernel is booked under kClsStage
 // RAII event bracket around one launch (no-op unless profiling)
 struct ProfScope {
   mamimo_engine* e; cudaStream_t st; int idx = -1;
@@ -593,6 +602,7 @@ mamimo_status check_flags(mamimo_engine* e, cudaStream_t st) {
     CK(e, cudaMemsetAsync(e->d_flags, 0, sizeof(uint32_t), st));
     if (f & kFlagTimeout) return fail(e, MAMIMO_ERR_TIMEOUT, "device pipeline wait timed out (kernel aborted)");
     if (f & kFlagRange) return fail(e, MAMIMO_ERR_RANGE, "fp16 split operand overflow: lower act_scale_log2 or use TF32X3");
+    if (f & kFlagNotPd) return fail(e, MAMIMO_ERR_RANGE, "LMMSE: Rpp is not positive definite in FP64 (SNR too high for this tau_rms)");
   }
   return MAMIMO_OK;
 }
@@ -898,7 +908,7 @@ void mamimo_destroy(mamimo_engine* e) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -1336,6 +1346,123 @@ mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype
                      mlp ? H_imag : nullptr, hb, mem, static_cast<cudaStream_t>(stream), stage);
 }
 
+// ---- next row: LMMSE smoother, LMMSE_ce.m:23-39 via helperMIMOChannelEstimate.m:37-39 ------------
+double mamimo_tau_rms(const double* h, int32_t n, int32_t is_complex) {
+  // LMMSE_ce.m:27-30: k = 0:n-1; hh = h*h'; tmp = |h|.^2 .* k; r = sum(tmp)/hh; r2 = tmp*k.'/hh; sqrt(r2 - r^2)
+  if (!h || n < 1) return 0.0;
+  double hh = 0, s1 = 0, s2 = 0;
+  for (int k = 0; k < n; ++k) {
+    const double p = is_complex ? h[2 * k] * h[2 * k] + h[2 * k + 1] * h[2 * k + 1] : h[k] * h[k];
+    hh += p; s1 += p * k; s2 += p * k * static_cast<double>(k);
+  }
+  const double r = s1 / hh, r2 = s2 / hh;
+  return std::sqrt(r2 - r * r);
+}
+
+mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_type, int64_t n_pkt,
+                           const double* tau_rms, const double* snr_db, void* H_mmse, mamimo_ctype out_type,
+                           mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (n_pkt < 0 || (n_pkt > 0 && (!H_ls || !H_mmse || !tau_rms || !snr_db))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(H_ls) | reinterpret_cast<uintptr_t>(H_mmse)) & 15) return fail(e, MAMIMO_ERR_INVALID, "H_ls and H_mmse must be 16-byte aligned");
+  if (n_pkt == 0) return MAMIMO_OK;
+  CK(e, cudaSetDevice(e->cfg.device));
+  const int n = e->cfg.n_sc, nt = e->cfg.n_tx, nrx = e->cfg.n_rx;
+  const int nb = (n + kLmNB - 1) / kLmNB, n_pad = nb * kLmNB, nt_pad = round_up(nt, 8), R = n_pad + nt_pad;
+  const int64_t n_slab = n_pkt * nrx;
+  const size_t per_slab = (static_cast<size_t>(R) * n_pad + static_cast<size_t>(nb) * kLmNB * kLmNB) * sizeof(double2);
+  if (!e->lm_M) {
+    size_t budget = static_cast<size_t>(8) << 30;                       // workspace budget (MAMIMO_LMMSE_WS_MB)
+    if (const char* env = getenv("MAMIMO_LMMSE_WS_MB")) if (atoll(env) > 0) budget = static_cast<size_t>(atoll(env)) << 20;
+    size_t free_b = 0, total_b = 0;
+    CK(e, cudaMemGetInfo(&free_b, &total_b));
+    budget = std::min(budget, free_b / 2);
+    const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(static_cast<int64_t>(budget / per_slab), 32768));
+    e->lm_slabs = static_cast<int>(std::min<int64_t>(cap, std::max<int64_t>(n_slab, 4LL * nrx)));
+    CK(e, cudaMalloc(&e->lm_M, static_cast<size_t>(e->lm_slabs) * R * n_pad * sizeof(double2)));
+    CK(e, cudaMalloc(&e->lm_Dinv, static_cast<size_t>(e->lm_slabs) * nb * kLmNB * kLmNB * sizeof(double2)));
+    CK(e, cudaMalloc(&e->lm_par, static_cast<size_t>(e->lm_slabs) * sizeof(double2)));
+    CK(e, cudaFuncSetAttribute(lmmse_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmPanelSmem));
+  }
+  const size_t in_el = h_type == MAMIMO_C128 ? 16 : 8, out_el = out_type == MAMIMO_C128 ? 16 : 8;
+  const size_t slab_el = static_cast<size_t>(nt) * n;
+  if (mem == MAMIMO_MEM_HOST && e->lm_io_bytes < static_cast<size_t>(e->lm_slabs) * slab_el * 16) {
+    if (e->lm_in) cudaFree(e->lm_in);
+    if (e->lm_out) cudaFree(e->lm_out);
+    e->lm_in = e->lm_out = nullptr;
+    e->lm_io_bytes = static_cast<size_t>(e->lm_slabs) * slab_el * 16;
+    CK(e, cudaMalloc(&e->lm_in, e->lm_io_bytes));
+    CK(e, cudaMalloc(&e->lm_out, e->lm_io_bytes));
+  }
+  cudaStream_t st = mem == MAMIMO_MEM_HOST ? e->s_comp : static_cast<cudaStream_t>(stream);
+  const double two_pi = 6.283185307179586476925286766559;
+  std::vector<double2> par;
+  for (int64_t s0 = 0; s0 < n_slab; s0 += e->lm_slabs) {
+    const int ns = static_cast<int>(std::min<int64_t>(e->lm_slabs, n_slab - s0));
+    par.resize(ns);
+    for (int i = 0; i < ns; ++i) {
+      const int64_t slab = s0 + i;
+      const double snr = std::pow(10.0, snr_db[slab] * 0.1);           // LMMSE_ce.m:23
+      par[i] = make_double2(two_pi * tau_rms[slab / nrx] / n, 1.0 / snr);   // j2pi_tau_df, LMMSE_ce.m:31-32
+    }
+    CK(e, cudaStreamSynchronize(st));                                  // previous chunk done with lm_par / staging
+    CK(e, cudaMemcpyAsync(e->lm_par, par.data(), ns * sizeof(double2), cudaMemcpyHostToDevice, st));
+    const char* in_p = static_cast<const char*>(H_ls) + s0 * slab_el * in_el;
+    char* out_p = static_cast<char*>(H_mmse) + s0 * slab_el * out_el;
+    LmArgs a;
+    memset(&a, 0, sizeof(a));
+    if (mem == MAMIMO_MEM_HOST) {
+      CK(e, cudaMemcpyAsync(e->lm_in, in_p, ns * slab_el * in_el, cudaMemcpyHostToDevice, st));
+      e->stats.h2d_bytes += ns * slab_el * in_el;
+      a.B = e->lm_in; a.out = e->lm_out;
+    } else {
+      a.B = in_p; a.out = out_p;
+    }
+    a.M = e->lm_M; a.Dinv = e->lm_Dinv; a.par = e->lm_par;
+    a.b_double = h_type == MAMIMO_C128; a.out_double = out_type == MAMIMO_C128;
+    a.n = n; a.n_pad = n_pad; a.nb = nb; a.n_tx = nt; a.nt_pad = nt_pad; a.R = R; a.n_ps = e->cfg.n_ps;
+    a.flags = e->d_flags;
+    {
+      ProfScope ps(e, st, kClsLmmse);
+      const int gx = static_cast<int>(std::min<size_t>((static_cast<size_t>(R) * n_pad + 255) / 256, 1024));
+      lmmse_fill_kernel<<<dim3(gx, ns), 256, 0, st>>>(a);
+    }
+    e->stats.kernel_launches++;
+    for (int J = 0; J < nb; ++J) {
+      a.J = J;
+      {
+        ProfScope ps(e, st, kClsLmmse);
+        lmmse_diag_kernel<<<ns, 256, 0, st>>>(a);
+      }
+      const int rows_below = R - (J + 1) * kLmNB;
+      {
+        ProfScope ps(e, st, kClsLmmse);
+        lmmse_panel_kernel<<<dim3((rows_below + kLmPanelRows - 1) / kLmPanelRows, ns), 256, kLmPanelSmem, st>>>(a);
+      }
+      e->stats.kernel_launches += 2;
+    }
+    {
+      ProfScope ps(e, st, kClsLmmse);
+      lmmse_backsub_kernel<<<dim3(nt_pad / 8, ns), 256, 0, st>>>(a);
+    }
+    e->stats.kernel_launches++;
+    if (e->cfg.n_ps != 1) {
+      ProfScope ps(e, st, kClsLmmse);
+      lmmse_rhp_kernel<<<dim3((n + 127) / 128, nt, ns), 128, 0, st>>>(a);
+      e->stats.kernel_launches++;
+    }
+    CK(e, cudaGetLastError());
+    if (mem == MAMIMO_MEM_HOST) {
+      CK(e, cudaMemcpyAsync(out_p, e->lm_out, ns * slab_el * out_el, cudaMemcpyDeviceToHost, st));
+      e->stats.d2h_bytes += ns * slab_el * out_el;
+    }
+  }
+  if (mem == MAMIMO_MEM_HOST) {
+    return check_flags(e, st);
+  }
+  return MAMIMO_OK;
+}
+
 mamimo_status mamimo_synchronize(mamimo_engine* e) {
   if (!e) return MAMIMO_ERR_INVALID;
   CK(e, cudaSetDevice(e->cfg.device));
@@ -1368,6 +1495,7 @@ mamimo_status mamimo_profile_end(mamimo_engine* e, mamimo_profile* out) {
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       if (r.cls == kClsLs) { out->ls_ms += ms; out->ls_launches++; }
       else if (r.cls == kClsFc) { out->fc_ms += ms; out->fc_launches++; }
+      else if (r.cls == kClsLmmse) { out->lmmse_ms += ms; out->lmmse_launches++; }
       else { out->stage_ms += ms; out->stage_launches++; }
     }
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);

@@ -104,6 +104,13 @@ __device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const float (
     uint32_t pk[Sch::kPlanes][kWords];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
+      if constexpr (S == kFp16x3) {
+        uint32_t w[2];
+        Sch::split2(v[j], v[j + 1], a.out_scale, w, &ovf);
+        pk[0][j >> 1] = w[0];
+        pk[1][j >> 1] = w[1];
+        continue;
+      }
       E p0[Sch::kPlanes], p1[Sch::kPlanes];
       Sch::split(v[j], a.out_scale, p0, &ovf);
       Sch::split(v[j + 1], a.out_scale, p1, &ovf);

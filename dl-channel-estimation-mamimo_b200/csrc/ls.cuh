@@ -100,6 +100,19 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
         }
       }
       if (a.planes[0]) {
+        if constexpr (S == kFp16x3) {
+          uint32_t r01[2], r23[2], i01[2], i23[2];
+          Sch::split2(re[0], re[1], a.scale, r01, &ovf);
+          Sch::split2(re[2], re[3], a.scale, r23, &ovf);
+          Sch::split2(im[0], im[1], a.scale, i01, &ovf);
+          Sch::split2(im[2], im[3], a.scale, i23, &ovf);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+            *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[0]) + off) = make_uint2(r01[pl], r23[pl]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[1]) + off) = make_uint2(i01[pl], i23[pl]);
+          }
+        } else {
         E pr[4][Sch::kPlanes], pi[4][Sch::kPlanes];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -121,6 +134,7 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
             *reinterpret_cast<uint2*>(d1) = make_uint2(bits(pi[0][pl]) | (bits(pi[1][pl]) << 16),
                                                        bits(pi[2][pl]) | (bits(pi[3][pl]) << 16));
           }
+        }
         }
       }
     }

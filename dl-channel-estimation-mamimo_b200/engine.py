@@ -320,6 +320,38 @@ class Engine:
             return Hls
         return (Hr, Hi, Hls) if want_ls else (Hr, Hi)
 
+    # ------------------------------------------------------------------ LMMSE smoother
+    def lmmse(self, H_ls, tau_rms, snr_db):
+        """LMMSE_ce over a batch (pg/LMMSE_ce.m:23-39 as called at pg/helperMIMOChannelEstimate.m:37-39).
+        H_ls [n_pkt, n_rx, n_tx, n_sc] complex64/128 (numpy = host, torch CUDA = device); tau_rms scalar or [n_pkt];
+        snr_db scalar, [n_rx] or [n_pkt, n_rx] (SNR(i) in dB).  Returns H_mmse, same shape / dtype / residence."""
+        c = self.cfg
+        if tuple(H_ls.shape[1:]) != (c.n_rx, c.n_tx, c.n_sc):
+            raise ValueError("H_ls must be [n_pkt, n_rx=%d, n_tx=%d, n_sc=%d]" % (c.n_rx, c.n_tx, c.n_sc))
+        n_pkt = int(H_ls.shape[0])
+        tau = np.ascontiguousarray(np.broadcast_to(np.asarray(tau_rms, dtype=np.float64), (n_pkt,)))
+        snr = np.ascontiguousarray(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (n_pkt, c.n_rx)))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        if _is_torch_cuda(H_ls):
+            import torch
+            if H_ls.dtype not in (torch.complex64, torch.complex128):
+                raise TypeError("H_ls must be complex64 or complex128")
+            H_ls = H_ls.contiguous()
+            out = torch.empty_like(H_ls)
+            t = _capi.C128 if H_ls.dtype == torch.complex128 else _capi.C64
+            check(lib.mamimo_lmmse(self._h, C.c_void_p(H_ls.data_ptr()), t, n_pkt, dp(tau), dp(snr),
+                                   C.c_void_p(out.data_ptr()), t, _capi.MEM_DEVICE,
+                                   C.c_void_p(torch.cuda.current_stream(H_ls.device).cuda_stream)), self._h)
+            return out
+        H_ls = np.ascontiguousarray(H_ls)
+        if H_ls.dtype not in (np.complex64, np.complex128):
+            raise TypeError("H_ls must be complex64 or complex128")
+        t = _capi.C128 if H_ls.dtype == np.complex128 else _capi.C64
+        out = np.empty_like(H_ls)
+        check(lib.mamimo_lmmse(self._h, _np_ptr(H_ls), t, n_pkt, dp(tau), dp(snr), _np_ptr(out), t, _capi.MEM_HOST, None),
+              self._h)
+        return out
+
     def synchronize(self):
         check(lib.mamimo_synchronize(self._h), self._h)
 
@@ -330,7 +362,8 @@ class Engine:
         p = _capi.Profile()
         check(lib.mamimo_profile_end(self._h, C.byref(p)), self._h)
         return dict(ls_ms=p.ls_ms, fc_ms=p.fc_ms, stage_ms=p.stage_ms, ls_launches=int(p.ls_launches),
-                    fc_launches=int(p.fc_launches), stage_launches=int(p.stage_launches))
+                    fc_launches=int(p.fc_launches), stage_launches=int(p.stage_launches),
+                    lmmse_ms=p.lmmse_ms, lmmse_launches=int(p.lmmse_launches))
 
     def stats(self):
         s = _capi.Stats()
@@ -383,6 +416,14 @@ def pair_row(p, i_rx, i_tx, n_rx, n_tx):
     return int(lib.mamimo_pair_row(p, i_rx, i_tx, n_rx, n_tx))
 
 
+def tau_rms(h):
+    """rms delay LMMSE_ce.m:27-30 derives from its `h` argument (real or complex vector)."""
+    h = np.asarray(h).ravel()
+    cplx = np.iscomplexobj(h)
+    buf = np.ascontiguousarray(h.astype(np.complex128).view(np.float64) if cplx else h.astype(np.float64))
+    return float(lib.mamimo_tau_rms(buf.ctypes.data_as(C.POINTER(C.c_double)), h.size, int(cplx)))
+
+
 # ---------------------------------------------------------------------- MATLAB-shaped drop-in
 _ENGINE_CACHE = {}
 
@@ -393,11 +434,12 @@ def helperMIMOChannelEstimate(rxData, prm, Nps=1, tau=None, SNR=None, isMMSE=Fal
     Same argument meaning as pg/helperMIMOChannelEstimate.m:1.  rxData complex [Nsc, nltf, Nr]
     (MATLAB logical shape) or [Nsc, nltf, Nr, Npkt] for a batch hoisted out of the packet loop;
     prm needs 'numSTS' and 'CarriersLocations' (1-based, :9,26).  Returns hD [Nsc, numSTS, Nr(, Npkt)]
-    complex128, P, ltf_o = ltf(ind) (:29) and hDmmse = zeros (LMMSE is out of scope: SURVEY 8f-3;
-    isMMSE=True raises NotImplementedError).
+    complex128, P, ltf_o = ltf(ind) (:29) and hDmmse (zeros unless isMMSE, as in the reference :32).  With
+    isMMSE, tau is LMMSE_ce's `h` vector (one per call, or a list of Npkt vectors for a batch) and SNR is SNR(i)
+    in dB, [Nr] or [Nr, Npkt] (:37-39).
     """
-    if isMMSE:
-        raise NotImplementedError("LMMSE_ce is outside the accelerated hot path (SURVEY.md 8f-3)")
+    if isMMSE and (tau is None or SNR is None):
+        raise ValueError("isMMSE needs tau and SNR (helperMIMOChannelEstimate.m:38)")
     get = (lambda k: prm[k]) if isinstance(prm, dict) else (lambda k: getattr(prm, k))
     num_sts = int(get("numSTS"))
     ind = np.asarray(get("CarriersLocations"), dtype=np.int64).ravel()
@@ -424,9 +466,19 @@ def helperMIMOChannelEstimate(rxData, prm, Nps=1, tau=None, SNR=None, isMMSE=Fal
     Y = np.ascontiguousarray(np.transpose(rx, (3, 2, 1, 0)).astype(np.complex128, copy=False))
     H = eng.ls_estimate(Y)                                   # [Npkt, Nr, Nt, Nsc]
     hD = np.transpose(H, (3, 2, 1, 0))
+    if isMMSE:
+        if Nps != 1 and Nps != eng.cfg.n_ps:
+            raise ValueError("Nps=%d: the cached LS engine was built for pilot spacing %d" % (Nps, eng.cfg.n_ps))
+        taus = tau if (isinstance(tau, (list, tuple)) and len(tau) == npkt and np.ndim(tau[0]) > 0) else [tau] * npkt
+        t_rms = np.array([tau_rms(t) for t in taus])
+        snr = np.asarray(SNR, dtype=np.float64)
+        snr = np.broadcast_to(snr.reshape(nrx, -1).T, (npkt, nrx))     # [Nr] or [Nr, Npkt] -> [Npkt, Nr]
+        hM = np.transpose(eng.lmmse(H, t_rms, snr), (3, 2, 1, 0))
+    else:
+        hM = np.zeros_like(hD)
     if squeeze:
-        hD = hD[..., 0]
-    return hD, Pm, ltf_o.reshape(-1, 1), np.zeros_like(hD)
+        hD, hM = hD[..., 0], hM[..., 0]
+    return hD, Pm, ltf_o.reshape(-1, 1), hM
 
 
 # ---------------------------------------------------------------------- inference.py drop-in

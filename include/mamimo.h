@@ -101,7 +101,7 @@ typedef struct {
   uint64_t kernel_launches;   /* engine kernels launched since create */
   uint64_t h2d_bytes;         /* bytes copied host->device by the engine */
   uint64_t d2h_bytes;
-  uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout */
+  uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout, bit2 LMMSE matrix not positive definite */
   uint32_t reserved;
 } mamimo_stats;
 
@@ -109,6 +109,8 @@ typedef struct {
 typedef struct {
   double ls_ms, fc_ms, stage_ms;                 /* summed event-to-event durations */
   uint64_t ls_launches, fc_launches, stage_launches;
+  double lmmse_ms;                               /* LMMSE smoother kernels (fill, diag, panel, backsub) */
+  uint64_t lmmse_launches;
 } mamimo_profile;
 
 /* ---- library-level ------------------------------------------------------- */
@@ -216,6 +218,20 @@ MAMIMO_API mamimo_status mamimo_ofdm_demod(mamimo_engine* e, const void* x, mami
 MAMIMO_API mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype x_type, int64_t n_pkt,
                                               void* H_ls, float* H_real, float* H_imag, mamimo_mem mem,
                                               void* stream);
+
+/* ---- next row: LMMSE smoother ---------------------------------
+ * Replaces the isMMSE branch of pg/helperMIMOChannelEstimate.m:37-39, i.e. LMMSE_ce(hD(:,j,i), Nsc, Nsc, Nps, tau,
+ * SNR(i)) (pg/LMMSE_ce.m:23-39) for every pair of a batch: H_mmse = Rhp * inv(Rpp) * H_ls with
+ * Rpp = 1./(1 + j*2*pi*tau_rms/Nsc*Nps*(k - k')) + eye/snr, Rhp = 1./(1 + j*2*pi*tau_rms/Nsc*(k - k'*Nps)).
+ * tau_rms [n_pkt] (host) is what LMMSE_ce.m:27-30 derives from its `h` argument (mamimo_tau_rms restates it),
+ * snr_db [n_pkt][n_rx] (host) is SNR(i) in dB.  H_ls / H_mmse complex [n_pkt][n_rx][n_tx][n_sc]; the pilot
+ * spacing is the engine's n_ps.  One FP64 Cholesky solve per (packet, rx) with the n_tx pairs as right-hand sides.
+ * MAMIMO_ERR_RANGE when a matrix is not positive definite in FP64 (device buffers: reported by mamimo_synchronize). */
+MAMIMO_API mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_type, int64_t n_pkt,
+                                      const double* tau_rms, const double* snr_db, void* H_mmse,
+                                      mamimo_ctype out_type, mamimo_mem mem, void* stream);
+/* tau_rms of LMMSE_ce.m:27-30 for h [n] (real, or complex interleaved when is_complex) */
+MAMIMO_API double mamimo_tau_rms(const double* h, int32_t n, int32_t is_complex);
 
 MAMIMO_API mamimo_status mamimo_synchronize(mamimo_engine* e);
 MAMIMO_API mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out);

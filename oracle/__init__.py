@@ -19,8 +19,10 @@ Pinning status (see DESIGN.md "Oracle"):
   graph) restate MATLAB / TensorFlow code that cannot run here (no MATLAB,
   Octave, TensorFlow, h5py): **parity unpinned** by execution of the
   reference; they are anchored on algebraic known-answer identities only.
+* ``oracle.lmmse`` (LMMSE_ce.m via helperMIMOChannelEstimate.m:37-39) restates MATLAB code: **parity
+  unpinned** by execution; anchored on the identities listed in its header.
 * ``oracle.interp`` has no reference counterpart at all (the reference always
   uses Nps = 1): **parity unpinned**, defined here.
 """
 
-from . import tables, ls, mlp, postproc, interp  # noqa: F401
+from . import tables, ls, mlp, postproc, interp, lmmse  # noqa: F401

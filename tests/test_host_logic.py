@@ -58,5 +58,5 @@ def test_helper_argument_validation_without_gpu():
         mm.helperMIMOChannelEstimate(np.zeros((100, 4, 2), np.complex128), prm)
     with pytest.raises(ValueError):                            # nltf should be == numSTS (:10)
         mm.helperMIMOChannelEstimate(np.zeros((234, 3, 2), np.complex128), prm)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                            # isMMSE needs tau and SNR (:38)
         mm.helperMIMOChannelEstimate(np.zeros((234, 4, 2), np.complex128), prm, 1, None, 10.0, True)

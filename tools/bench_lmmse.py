@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Measurement of the LMMSE smoother at the reference numerology (32x4, 234 tones) and at the
+bench shape (32x4, 1024 tones): packets/s, FP64 FLOP rate (algorithmic: Cholesky n^3/3 + 2 triangular solves with
+Nt right-hand sides, 8 flops per complex MAC), and the numpy restatement of LMMSE_ce.m on the host beside it.
+Test infrastructure (imports oracle)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import mamimo_b200 as mm
+from oracle import lmmse
+
+for name, nt, nr, nsc, npkt, cpu_pairs in (("ref-numerology 32x4x234", 32, 4, 234, 500, 8), ("config-2 shape 32x4x1024", 32, 4, 1024, 32, 1)):
+    rng = np.random.default_rng(2)
+    H = (rng.standard_normal((npkt, nr, nt, nsc)) + 1j * rng.standard_normal((npkt, nr, nt, nsc))).astype(np.complex64)
+    t_rms = rng.uniform(1.0, 5.0, npkt)
+    snr = rng.uniform(0.0, 20.0, (npkt, nr))
+    Hd = torch.from_numpy(H).cuda()
+    with mm.Engine(nt, nr, nsc, mlp=False) as eng:
+        for _ in range(2):
+            out = eng.lmmse(Hd, t_rms, snr)
+        torch.cuda.synchronize()
+        eng.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            out = eng.lmmse(Hd, t_rms, snr)
+        e1.record()
+        torch.cuda.synchronize()
+        prof = eng.profile_end()
+        ms = e0.elapsed_time(e1) / reps
+    ref = lmmse.lmmse_batched(H[:1], t_rms[:1], snr[:1])
+    err = float(np.linalg.norm(out[:1].cpu().numpy() - ref) / np.linalg.norm(ref))
+    n = nsc
+    cmac = n ** 3 / 3.0 + 2 * nt * n * n / 2.0                      # per (pkt, rx) slab
+    flops = 8.0 * cmac * npkt * nr
+    # CPU: the reference rebuilds + inverts per PAIR (LMMSE_ce.m is called inside the tx loop): time a few pairs
+    t0 = time.perf_counter()
+    for j in range(cpu_pairs):
+        lmmse.lmmse_ce(H[0, 0, j % nt].astype(np.complex128), n, n, 1, np.array([1.0, 0, 0, 1]), 10.0)
+    cpu_pair_s = (time.perf_counter() - t0) / cpu_pairs
+    print(json.dumps({"case": name, "pkts": npkt, "ms": ms, "packets_per_s": npkt / (ms * 1e-3), "rel_l2_vs_oracle": err,
+                      "fp64_tflops_algorithmic": flops / (ms * 1e-3) / 1e12, "kernel_ms_sum": prof["lmmse_ms"] / reps,
+                      "launches": prof["lmmse_launches"] // reps,
+                      "cpu_numpy_s_per_packet_literal": cpu_pair_s * nt * nr, "cpu_cores": os.cpu_count(),
+                      "reference_published_s_per_packet": 1.139 if nsc == 234 else None}), flush=True)
