@@ -11,7 +11,8 @@
 // (tau_rms) and the rx antenna (SNR(i)), so one "slab" = (packet, rx) is ONE Hermitian positive-definite system
 // with the Nt LS vectors as right-hand sides.  Everything is FP64 (cond(Rpp) ~ Nsc * snr rules FP32 out):
 //
-//   M = [ Rpp ; B^H ]   (n_pad + nt_pad) x n_pad, row-major double2, one per slab       lmmse_fill_kernel
+//   M = [ Rpp ; B^H ]   (n_pad + nt_pad) x n_pad, row-major double2, one per slab; its entries are generated on
+//   the fly (lm_elem), the buffer only ever holds the factor L and the solved right-hand sides
 //   blocked LEFT-looking Cholesky over 32-column blocks J (each output written once, accumulators in registers):
 //     D   = Rpp_JJ - sum_{K<J} L_JK L_JK^H ;  L_JJ = chol(D) ;  Linv_JJ = L_JJ^-1       lmmse_diag_kernel
 //     X_J = (M_J - sum_{K<J} L_K L_JK^H) Linv_JJ^H   for all rows below, B^H rows too   lmmse_panel_kernel
@@ -65,39 +66,30 @@ __device__ __forceinline__ double2 corr(double x) {
   return make_double2(d, -x * d);
 }
 
-// ---- M = [Rpp (lower triangle) ; conj(B)^T rows] -----------------------------------------------------------
-__global__ void __launch_bounds__(256) lmmse_fill_kernel(const LmArgs a) {
-  const int slab = blockIdx.y;
-  const double2 cs = a.par[slab];
-  double2* M = a.M + static_cast<size_t>(slab) * a.R * a.n_pad;
-  const size_t total = static_cast<size_t>(a.R) * a.n_pad;
-  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int i = static_cast<int>(idx / a.n_pad), j = static_cast<int>(idx - static_cast<size_t>(i) * a.n_pad);
-    double2 v = make_double2(0.0, 0.0);
-    if (i < a.n_pad) {
-      if (j > i) continue;                                   // upper triangle is never read
-      if (i < a.n && j < a.n) {
-        v = corr(cs.x * a.n_ps * static_cast<double>(i - j));  // rf2(i, j)   LMMSE_ce.m:35-36
-        if (i == j) v.x += cs.y;                             // + eye / snr   LMMSE_ce.m:38
-      } else if (i == j) {
-        v.x = 1.0;                                           // padding: identity block, decoupled
-      }
-    } else {
-      const int t = i - a.n_pad;
-      if (t < a.n_tx && j < a.n) {
-        const size_t g = (static_cast<size_t>(slab) * a.n_tx + t) * a.n + j;
-        if (a.b_double) {
-          const double2 b = reinterpret_cast<const double2*>(a.B)[g];
-          v = make_double2(b.x, -b.y);
-        } else {
-          const float2 b = reinterpret_cast<const float2*>(a.B)[g];
-          v = make_double2(b.x, -static_cast<double>(b.y));
-        }
+// ---- element (i, j) of [Rpp ; B^H], generated on the fly (no fill pass, M only ever holds L) ----------------------
+__device__ __forceinline__ double2 lm_elem(const LmArgs& a, int slab, double2 cs, int i, int j) {
+  double2 v = make_double2(0.0, 0.0);
+  if (i < a.n_pad) {
+    if (i < a.n && j < a.n) {
+      v = corr(cs.x * a.n_ps * static_cast<double>(i - j));    // rf2(i, j)   LMMSE_ce.m:35-36
+      if (i == j) v.x += cs.y;                                 // + eye / snr   LMMSE_ce.m:38
+    } else if (i == j) {
+      v.x = 1.0;                                               // padding: identity block, decoupled
+    }
+  } else {
+    const int t = i - a.n_pad;                                 // appended rows: conj(B)^T
+    if (t < a.n_tx && j < a.n) {
+      const size_t g = (static_cast<size_t>(slab) * a.n_tx + t) * a.n + j;
+      if (a.b_double) {
+        const double2 b = reinterpret_cast<const double2*>(a.B)[g];
+        v = make_double2(b.x, -b.y);
+      } else {
+        const float2 b = reinterpret_cast<const float2*>(a.B)[g];
+        v = make_double2(b.x, -static_cast<double>(b.y));
       }
     }
-    M[idx] = v;
   }
+  return v;
 }
 
 // ---- diagonal block J: Schur update, Cholesky, inverse ----------------------------------------------------------
@@ -106,6 +98,7 @@ __global__ void __launch_bounds__(256) lmmse_diag_kernel(const LmArgs a) {
   __shared__ double2 D[kLmNB][kLmPitch];
   double2 (*Lo)[kLmPitch] = Lt;
   const int slab = blockIdx.x;
+  const double2 cs = a.par[slab];
   double2* M = a.M + static_cast<size_t>(slab) * a.R * a.n_pad;
   const int Jb = a.J * kLmNB;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;     // outputs (ty + 16 i, tx + 16 j), i, j < 2
@@ -133,7 +126,7 @@ __global__ void __launch_bounds__(256) lmmse_diag_kernel(const LmArgs a) {
     for (int j = 0; j < 2; ++j) {
       const int r = ty + 16 * i, c = tx + 16 * j;
       double2 v = make_double2(0.0, 0.0);
-      if (c <= r) v = zsub(M[static_cast<size_t>(Jb + r) * a.n_pad + Jb + c], acc[i][j]);
+      if (c <= r) v = zsub(lm_elem(a, slab, cs, Jb + r, Jb + c), acc[i][j]);
       D[r][c] = v;
       Lo[r][c] = make_double2(0.0, 0.0);
     }
@@ -167,18 +160,25 @@ __global__ void __launch_bounds__(256) lmmse_diag_kernel(const LmArgs a) {
     const int r = e >> 5, c = e & 31;
     if (c <= r) M[static_cast<size_t>(Jb + r) * a.n_pad + Jb + c] = Lo[r][c];
   }
-  // Linv = Lo^-1 (lower triangular): thread c solves Lo x = e_c by forward substitution, x kept in column c of D
-  if (threadIdx.x < kLmNB) {
-    const int c = threadIdx.x;
+  // Linv = Lo^-1 (lower triangular), column c by forward substitution  x_r = (delta_rc - sum_{c<=m<r} Lo[r][m] x_m) / Lo[r][r].
+  // 8 lanes share one column (the sum over m is split 8 ways and reduced with shuffles), 4 columns per warp; x is
+  // kept in column c of D, which only this column's lanes touch.
+  {
+    const int c = threadIdx.x >> 3, hlp = threadIdx.x & 7;
     for (int r = 0; r < kLmNB; ++r) {
-      double2 s = make_double2(r == c ? 1.0 : 0.0, 0.0);
-      for (int m = c; m < r; ++m) {                           // x_m = 0 for m < c
-        const double2 l = Lo[r][m], x = D[m][c];
-        s.x -= l.x * x.x - l.y * x.y;
-        s.y -= l.x * x.y + l.y * x.x;
+      double2 sum = make_double2(0.0, 0.0);
+      for (int m = c + hlp; m < r; m += 8) zmac(sum, Lo[r][m], D[m][c]);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
       }
-      const double inv = 1.0 / Lo[r][r].x;
-      D[r][c] = (r < c) ? make_double2(0.0, 0.0) : make_double2(s.x * inv, s.y * inv);
+      if (hlp == 0) {
+        const double inv = 1.0 / Lo[r][r].x;
+        D[r][c] = (r < c) ? make_double2(0.0, 0.0)
+                          : make_double2(((r == c ? 1.0 : 0.0) - sum.x) * inv, -sum.y * inv);
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) lmmse_panel_kernel(const LmArgs a) {
   double2 (*As)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem);
   double2 (*Bs)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem + kLmPanelRows * kLmPitch);
   const int slab = blockIdx.y;
+  const double2 cs = a.par[slab];
   double2* M = a.M + static_cast<size_t>(slab) * a.R * a.n_pad;
   const int Jb = a.J * kLmNB;
   const int row0 = Jb + kLmNB + blockIdx.x * kLmPanelRows;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256) lmmse_panel_kernel(const LmArgs a) {
     for (int j = 0; j < 2; ++j) {
       const int r = row0 + ty + 16 * i;
       double2 v = make_double2(0.0, 0.0);
-      if (r < a.R) v = zsub(M[static_cast<size_t>(r) * a.n_pad + Jb + tx + 16 * j], acc[i][j]);
+      if (r < a.R) v = zsub(lm_elem(a, slab, cs, r, Jb + tx + 16 * j), acc[i][j]);
       As[ty + 16 * i][tx + 16 * j] = v;
     }
   const double2* Di = a.Dinv + (static_cast<size_t>(slab) * a.nb + a.J) * kLmNB * kLmNB;
@@ -266,49 +267,100 @@ __global__ void __launch_bounds__(256) lmmse_panel_kernel(const LmArgs a) {
     }
 }
 
-// ---- back substitution, one warp per right-hand side: z L = y, from the last block to the first ---------------------
-__global__ void __launch_bounds__(256) lmmse_backsub_kernel(const LmArgs a) {
+// ---- back substitution  Z^H = Y^H L^-1  as a blocked GEMM: one CTA = 32 right-hand sides of one slab ----------------
+//   for J = last .. 0:   z_J = ( y_J - sum_{I > J} z_I L[I][J] ) Linv_JJ
+// The 32 x 32 tiles of z (rows = right-hand sides) and of L are staged in shared memory and shared by all 32
+// right-hand sides (the first version, one warp per right-hand side chasing z through L2, took 40 % of the whole
+// smoother).  128 threads, 4 x 2 outputs each, next tiles prefetched into registers.
+constexpr int kLmBsSmem = 4 * kLmNB * kLmPitch * 16;
+__global__ void __launch_bounds__(128) lmmse_backsub_kernel(const LmArgs a) {
+  extern __shared__ double2 lm_smem[];
+  double2 (*Zs)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem);
+  double2 (*Ls)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem + kLmNB * kLmPitch);
+  double2 (*Vs)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem + 2 * kLmNB * kLmPitch);
+  double2 (*Li)[kLmPitch] = reinterpret_cast<double2 (*)[kLmPitch]>(lm_smem + 3 * kLmNB * kLmPitch);
   const int slab = blockIdx.y;
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= a.nt_pad) return;
+  const int t0 = blockIdx.x * 32;
   double2* M = a.M + static_cast<size_t>(slab) * a.R * a.n_pad;
-  double2* z = M + static_cast<size_t>(a.n_pad + t) * a.n_pad;       // y on entry, z on exit (in place)
+  double2* Zg = M + static_cast<size_t>(a.n_pad + t0) * a.n_pad;     // rows t0.. : y on entry, z on exit (in place)
+  const int n_rows = min(32, a.nt_pad - t0);
   const double s = a.par[slab].y;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;           // outputs (ty + 8 i, tx + 16 j), i < 4, j < 2
+  const int lr = threadIdx.x >> 5, lk = threadIdx.x & 31;           // loader: rows lr + 4 q, column lk
+  double2 pz[8], pl[8];
   for (int J = a.nb - 1; J >= 0; --J) {
     const int Jb = J * kLmNB;
-    double2 v0 = z[Jb + lane], v1 = make_double2(0.0, 0.0), v2 = v1, v3 = v1;
-    int i = Jb + kLmNB;
-    for (; i + 3 < a.n_pad; i += 4) {                                // v -= z[i] * L[i][Jb + lane]
-      const double2 z0 = __ldcg(z + i), z1 = __ldcg(z + i + 1), z2 = __ldcg(z + i + 2), z3 = __ldcg(z + i + 3);
-      const double2* Lr = M + static_cast<size_t>(i) * a.n_pad + Jb + lane;
-      const double2 l0 = Lr[0], l1 = Lr[a.n_pad], l2 = Lr[2 * static_cast<size_t>(a.n_pad)], l3 = Lr[3 * static_cast<size_t>(a.n_pad)];
-      zmac(v0, make_double2(-z0.x, -z0.y), l0);
-      zmac(v1, make_double2(-z1.x, -z1.y), l1);
-      zmac(v2, make_double2(-z2.x, -z2.y), l2);
-      zmac(v3, make_double2(-z3.x, -z3.y), l3);
+    double2 acc[4][2] = {};
+    auto fetch = [&](int Ib) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = lr + 4 * q;
+        pz[q] = (r < n_rows) ? Zg[static_cast<size_t>(r) * a.n_pad + Ib + lk] : make_double2(0.0, 0.0);
+        pl[q] = M[static_cast<size_t>(Ib + r) * a.n_pad + Jb + lk];
+      }
+    };
+    if (J + 1 < a.nb) fetch(Jb + kLmNB);
+    for (int I = J + 1; I < a.nb; ++I) {
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { Zs[lr + 4 * q][lk] = pz[q]; Ls[lr + 4 * q][lk] = pl[q]; }
+      __syncthreads();
+      if (I + 1 < a.nb) fetch((I + 1) * kLmNB);
+#pragma unroll 4
+      for (int ii = 0; ii < kLmNB; ++ii) {
+        double2 zv[4], lv[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) zv[i] = Zs[ty + 8 * i][ii];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) lv[j] = Ls[ii][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) zmac(acc[i][j], zv[i], lv[j]);
+      }
     }
-    const double2 v = zadd(zadd(v0, v1), zadd(v2, v3));              // n_pad is a multiple of 32: no remainder loop
-    // z_J = v_J Linv_JJ :  z[c] = sum_{m >= c} v[m] Linv[m][c]
+    // v = y_J - acc -> Vs ;  Linv_JJ -> Li ;  z_J = v Linv_JJ
     const double2* Di = a.Dinv + (static_cast<size_t>(slab) * a.nb + J) * kLmNB * kLmNB;
-    double2 zc = make_double2(0.0, 0.0);
-#pragma unroll 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = ty + 8 * i, c = tx + 16 * j;
+        Vs[r][c] = (r < n_rows) ? zsub(Zg[static_cast<size_t>(r) * a.n_pad + Jb + c], acc[i][j]) : make_double2(0.0, 0.0);
+      }
+    for (int e = threadIdx.x; e < kLmNB * kLmNB; e += 128) Li[e >> 5][e & 31] = Di[e];
+    __syncthreads();
+    double2 z[4][2] = {};
+#pragma unroll 4
     for (int m = 0; m < kLmNB; ++m) {
-      const double2 vm = make_double2(__shfl_sync(0xffffffffu, v.x, m), __shfl_sync(0xffffffffu, v.y, m));
-      zmac(zc, vm, Di[m * kLmNB + lane]);                            // Linv[m][lane] == 0 for m < lane
+      double2 vv[4], lv[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vv[i] = Vs[ty + 8 * i][m];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) lv[j] = Li[m][tx + 16 * j];       // Linv[m][c] == 0 for m < c
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) zmac(z[i][j], vv[i], lv[j]);
     }
-    __stcg(z + Jb + lane, zc);
-    __syncwarp();
-    const int k = Jb + lane;
-    if (a.n_ps == 1 && t < a.n_tx && k < a.n) {                      // H_mmse = B - conj(z) / snr
-      const size_t g = (static_cast<size_t>(slab) * a.n_tx + t) * a.n + k;
-      double2 b;
-      if (a.b_double) b = reinterpret_cast<const double2*>(a.B)[g];
-      else { const float2 f = reinterpret_cast<const float2*>(a.B)[g]; b = make_double2(f.x, f.y); }
-      const double2 h = make_double2(b.x - s * zc.x, b.y + s * zc.y);
-      if (a.out_double) reinterpret_cast<double2*>(a.out)[g] = h;
-      else reinterpret_cast<float2*>(a.out)[g] = make_float2(static_cast<float>(h.x), static_cast<float>(h.y));
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = ty + 8 * i, k = Jb + tx + 16 * j, t = t0 + r;
+        if (r >= n_rows) continue;
+        Zg[static_cast<size_t>(r) * a.n_pad + k] = z[i][j];
+        if (a.n_ps == 1 && t < a.n_tx && k < a.n) {                  // H_mmse = B - conj(z) / snr
+          const size_t g = (static_cast<size_t>(slab) * a.n_tx + t) * a.n + k;
+          double2 b;
+          if (a.b_double) b = reinterpret_cast<const double2*>(a.B)[g];
+          else { const float2 f = reinterpret_cast<const float2*>(a.B)[g]; b = make_double2(f.x, f.y); }
+          const double2 h = make_double2(b.x - s * z[i][j].x, b.y + s * z[i][j].y);
+          if (a.out_double) reinterpret_cast<double2*>(a.out)[g] = h;
+          else reinterpret_cast<float2*>(a.out)[g] = make_float2(static_cast<float>(h.x), static_cast<float>(h.y));
+        }
+      }
+    __syncthreads();                                                 // z_J visible to the next block's tile loads
   }
 }
 

@@ -6,6 +6,8 @@
 //   mamimo_mex('finalize')
 //   hD = mamimo_mex('ls', rxData)                  rxData complex double [Nsc x nltf x Nr (x Npkt)]
 //   [hD, Hr, Hi] = mamimo_mex('estimate', rxData)  Hr/Hi single [Nsc x Nt*Nr*Npkt] (column = pair row)
+//   hM = mamimo_mex('lmmse', hD, tau, SNR)         LMMSE_ce over all pairs: tau = the `h` vector of LMMSE_ce (one per call)
+//                                                  or a [Ntau x Npkt] matrix, SNR(i) in dB [Nr (x Npkt)]
 //   ltf = mamimo_mex('ltf')                        256 x 1 tone table (no engine needed)
 //   mamimo_mex('destroy')
 //
@@ -131,6 +133,33 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       fail(mamimo_estimate(g_engine, mxGetComplexDoubles(prhs[1]), MAMIMO_C128, (int64_t)np, NULL,
                            mxGetSingles(plhs[1]), mxGetSingles(plhs[2]), MAMIMO_MEM_HOST, NULL));
     }
+  } else if (!strcmp(cmd, "lmmse")) {            // isMMSE branch of pg/helperMIMOChannelEstimate.m:37-39
+    need_engine();
+    if (nrhs < 4) mexErrMsgIdAndTxt("mamimo:usage", "hM = mamimo_mex('lmmse', hD, tau, SNR)");
+    const mxArray* hd = prhs[1];
+    if (!mxIsComplex(hd) || !mxIsDouble(hd)) mexErrMsgIdAndTxt("mamimo:type", "hD must be complex double");
+    const mwSize nd = mxGetNumberOfDimensions(hd);
+    const mwSize* d = mxGetDimensions(hd);
+    const mwSize nr = nd >= 3 ? d[2] : 1, np = nd >= 4 ? d[3] : 1;
+    if (nd > 4 || d[0] != (mwSize)g_cfg.n_sc || d[1] != (mwSize)g_cfg.n_tx || nr != (mwSize)g_cfg.n_rx)
+      mexErrMsgIdAndTxt("mamimo:size", "hD must be [Nsc x numSTS x Nr (x Npkt)]");
+    if (!mxIsDouble(prhs[2]) || !mxIsDouble(prhs[3]) || mxIsComplex(prhs[3]))
+      mexErrMsgIdAndTxt("mamimo:type", "tau must be double, SNR real double");
+    const size_t n_tau_all = mxGetNumberOfElements(prhs[2]), n_snr = mxGetNumberOfElements(prhs[3]);
+    if (n_snr != (size_t)nr && n_snr != (size_t)(nr * np)) mexErrMsgIdAndTxt("mamimo:size", "SNR must be [Nr] or [Nr x Npkt]");
+    const bool tau_per_pkt = np > 1 && mxGetN(prhs[2]) == np && mxGetM(prhs[2]) > 1;
+    const size_t n_tau = tau_per_pkt ? mxGetM(prhs[2]) : n_tau_all;
+    static double t_rms[65536], snr[65536];
+    if (np > 65536 || nr * np > 65536) mexErrMsgIdAndTxt("mamimo:size", "batch too large for one call");
+    const int cplx = mxIsComplex(prhs[2]);
+    const double* tp = cplx ? (const double*)mxGetComplexDoubles(prhs[2]) : mxGetDoubles(prhs[2]);
+    for (mwSize p = 0; p < np; ++p)
+      t_rms[p] = mamimo_tau_rms(tp + (tau_per_pkt ? p * n_tau * (cplx ? 2 : 1) : 0), (int32_t)n_tau, cplx);
+    for (mwSize p = 0; p < np; ++p)                   // MATLAB [Nr x Npkt] column-major == [pkt][rx]
+      for (mwSize i = 0; i < nr; ++i) snr[p * nr + i] = mxGetDoubles(prhs[3])[n_snr == (size_t)nr ? i : p * nr + i];
+    plhs[0] = mxCreateNumericArray(nd, d, mxDOUBLE_CLASS, mxCOMPLEX);
+    fail(mamimo_lmmse(g_engine, mxGetComplexDoubles(hd), MAMIMO_C128, (int64_t)np, t_rms, snr,
+                      mxGetComplexDoubles(plhs[0]), MAMIMO_C128, MAMIMO_MEM_HOST, NULL));
   } else {
     mexErrMsgIdAndTxt("mamimo:usage", "unknown command '%s'", cmd);
   }

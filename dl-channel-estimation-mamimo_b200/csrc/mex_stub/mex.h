@@ -17,6 +17,8 @@ typedef enum { mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7 } mxClassID;
 mwSize mxGetNumberOfDimensions(const mxArray*);
 const mwSize* mxGetDimensions(const mxArray*);
 size_t mxGetNumberOfElements(const mxArray*);
+size_t mxGetM(const mxArray*);
+size_t mxGetN(const mxArray*);
 int mxIsComplex(const mxArray*);
 int mxIsDouble(const mxArray*);
 int mxIsSingle(const mxArray*);

@@ -17,7 +17,8 @@ end
 mamimo_mex('pilots', double(ltf_o), double(P(1:numSTS,1:numSTS)));
 hD = mamimo_mex('ls', complex(double(rxData)));
 hDmmse = complex(zeros(size(hD)));
-if isMMSE
-    error('mamimo:unsupported','LMMSE_ce is outside the accelerated hot path; call the original helper for isMMSE=true');
+if isMMSE                                   % LMMSE_ce for every pair (:37-39), one FP64 solve per (packet, rx)
+    if Nps ~= 1, error('mamimo:unsupported','create the engine with n_ps = Nps for comb pilots'); end
+    hDmmse = mamimo_mex('lmmse', hD, double(tau), double(SNR));
 end
 end
