@@ -71,6 +71,8 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
+  int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
   int ls_tile = 64;             // tones per CTA of the split LS kernel (MAMIMO_LS_TILE=128: experiment)
   bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
   unsigned long long* d_dbg = nullptr;   // MAMIMO_FC_DEBUG=1: role wait-cycle counters of the pair kernel
@@ -292,8 +294,45 @@ mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st
   return MAMIMO_OK;
 }
 
+// TMA-fed persistent LS kernel: per-call tensor map over Y viewed as float32 [n_pkt*n_rx*n_ltf][2*n_sc]
+template <int S, int NLTF>
+mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2) * a.n_sc, static_cast<cuuint64_t>(a.n_pkt) * a.n_rx * a.n_ltf};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.n_sc) * 8};
+  const cuuint32_t box[2] = {128, static_cast<cuuint32_t>(NLTF)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(a.Y), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (LS) failed: " + std::to_string(r));
+  constexpr int smem = ls_tma_smem_bytes<NLTF>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int n_tiles = (a.n_pil + 63) / 64;
+  const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
+  const int per_sm = std::max(1, std::min(e->ls_tma_ctas, (227 * 1024) / (smem + 1024)));
+  const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(e->num_sms) * per_sm));
+  {
+    ProfScope ps(e, st, kClsLs);
+    ls_tma_kernel<S, NLTF><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
+  }
+  CK(e, cudaGetLastError());
+  e->stats.kernel_launches++;
+  return MAMIMO_OK;
+}
+
 template <int S>
 mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
+  if (e->hadamard && a.n_ps == 1 && e->ls_split && e->ls_tma && !a.y_double && (a.n_sc % 2) == 0) {
+    if (a.n_ltf == 32) return launch_ls_tma<S, 32>(e, a, st);
+    if (a.n_ltf == 64) return launch_ls_tma<S, 64>(e, a, st);
+  }
   // every reference call site (n_ps = 1, Hadamard P, 32 or 64 antennas): transform split over threads
   if (e->hadamard && a.n_ps == 1 && e->ls_split) {
     if (a.n_ltf == 32) return e->ls_tile == 128 ? launch_ls_split<S, 32, 128>(e, a, st) : launch_ls_split<S, 32, 64>(e, a, st);
@@ -826,6 +865,8 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;
   if (const char* env = getenv("MAMIMO_FC_DEBUG")) {
     if (atoi(env) && cudaMalloc(&e->d_dbg, 8 * sizeof(unsigned long long)) == cudaSuccess)

@@ -103,7 +103,8 @@ def test_helper_mimo_channel_estimate_dropin():
     assert hD.shape == (234, nt, nr) and hD.dtype == np.complex128 and ltf_o.shape == (234, 1)
     assert np.array_equal(ltf_o[:, 0], x)
     assert rel_l2(ls.ls_estimate_loop(rx_data, P, x), hD) <= TOL_LS
-    with pytest.raises(NotImplementedError):
+    assert not hDmmse.any()                                          # isMMSE = false: zeros (:32)
+    with pytest.raises(ValueError):                                  # isMMSE needs tau (LMMSE: tests/test_gpu_lmmse.py)
         mm.helperMIMOChannelEstimate(rx_data, prm, 1, None, 10.0, True)
 
 
