@@ -71,7 +71,9 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  bool ofdm_tma = true;         // persistent bulk-copy-fed OFDM kernel (MAMIMO_OFDM_TMA=0: plain three-pass kernel)
   bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
+  int ls_tma_stages = 2;        // stage buffers per CTA (MAMIMO_LS_TMA_STAGES = 2 | 3)
   int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
   int ls_tile = 64;             // tones per CTA of the split LS kernel (MAMIMO_LS_TILE=128: experiment)
   bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
@@ -295,7 +297,7 @@ mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st
 }
 
 // TMA-fed persistent LS kernel: per-call tensor map over Y viewed as float32 [n_pkt*n_rx*n_ltf][2*n_sc]
-template <int S, int NLTF>
+template <int S, int NLTF, int STAGES>
 mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -308,10 +310,10 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (LS) failed: " + std::to_string(r));
-  constexpr int smem = ls_tma_smem_bytes<NLTF>();
+  constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
-    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int n_tiles = (a.n_pil + 63) / 64;
@@ -320,7 +322,7 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
   const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(e->num_sms) * per_sm));
   {
     ProfScope ps(e, st, kClsLs);
-    ls_tma_kernel<S, NLTF><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
+    ls_tma_kernel<S, NLTF, STAGES><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
   }
   CK(e, cudaGetLastError());
   e->stats.kernel_launches++;
@@ -330,8 +332,8 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
 template <int S>
 mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   if (e->hadamard && a.n_ps == 1 && e->ls_split && e->ls_tma && !a.y_double && (a.n_sc % 2) == 0) {
-    if (a.n_ltf == 32) return launch_ls_tma<S, 32>(e, a, st);
-    if (a.n_ltf == 64) return launch_ls_tma<S, 64>(e, a, st);
+    if (a.n_ltf == 32) return e->ls_tma_stages == 3 ? launch_ls_tma<S, 32, 3>(e, a, st) : launch_ls_tma<S, 32, 2>(e, a, st);
+    if (a.n_ltf == 64) return e->ls_tma_stages == 3 ? launch_ls_tma<S, 64, 3>(e, a, st) : launch_ls_tma<S, 64, 2>(e, a, st);
   }
   // every reference call site (n_ps = 1, Hadamard P, 32 or 64 antennas): transform split over threads
   if (e->hadamard && a.n_ps == 1 && e->ls_split) {
@@ -566,6 +568,24 @@ mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps
 }
 
 mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n_pkt, float2* dY, cudaStream_t st) {
+  if (e->fft_len == 256 && e->d_tw256 && !x_double && e->ofdm_tma && (e->cp_len % 2) == 0 && (e->sym_offset % 2) == 0 &&
+      getenv("MAMIMO_OFDM_GENERIC") == nullptr) {
+    OfdmR16Args b;
+    memset(&b, 0, sizeof(b));
+    b.x = dx; b.Y = dY; b.tw2 = e->d_tw256; b.tw3 = nullptr; b.kmap = e->d_kmap;
+    b.cp_len = e->cp_len; b.sym_offset = e->sym_offset; b.n_sc = e->cfg.n_sc;
+    b.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf; b.x_double = 0; b.flags = e->d_flags;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((b.total_syms + 15) / 16, static_cast<long long>(e->num_sms) * 3));
+    static bool set = false;
+    if (!set) { CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<8>())); set = true; }
+    {
+      ProfScope ps(e, st, kClsStage);
+      ofdm_r16_tma_kernel<8><<<grid, 256, ofdm_r16_tma_smem<8>(), st>>>(b);
+    }
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return MAMIMO_OK;
+  }
   if (e->fft_len == 256 && e->d_tw256 && getenv("MAMIMO_OFDM_GENERIC") == nullptr) {
     Ofdm256Args b;
     memset(&b, 0, sizeof(b));
@@ -589,6 +609,28 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
     b.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf; b.x_double = x_double;
     const int syms = 4096 / e->fft_len;
     const unsigned grid = static_cast<unsigned>((b.total_syms + syms - 1) / syms);
+    b.flags = e->d_flags;
+    if (!x_double && e->ofdm_tma && (e->cp_len % 2) == 0 && (e->sym_offset % 2) == 0) {
+      // persistent kernel, next tile's FFT windows prefetched by cp.async.bulk
+      const unsigned pgrid = std::min<unsigned>(grid, static_cast<unsigned>(e->num_sms) * 3u);
+      ProfScope ps(e, st, kClsStage);
+#define OFDM_TMA_CASE(L)                                                                                              \
+  {                                                                                                                   \
+    static bool set = false;                                                                                          \
+    if (!set) { CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<L>())); set = true; } \
+    ofdm_r16_tma_kernel<L><<<pgrid, 256, ofdm_r16_tma_smem<L>(), st>>>(b);                                            \
+  }
+      switch (e->fft_len) {
+        case 512: OFDM_TMA_CASE(9) break;
+        case 1024: OFDM_TMA_CASE(10) break;
+        case 2048: OFDM_TMA_CASE(11) break;
+        default: OFDM_TMA_CASE(12) break;
+      }
+#undef OFDM_TMA_CASE
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches++;
+      return MAMIMO_OK;
+    }
     {
       ProfScope ps(e, st, kClsStage);
       switch (e->fft_len) {
@@ -866,6 +908,8 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_TMA_STAGES")) e->ls_tma_stages = atoi(env) == 3 ? 3 : 2;
   if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;
   if (const char* env = getenv("MAMIMO_FC_DEBUG")) {

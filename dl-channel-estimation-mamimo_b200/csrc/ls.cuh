@@ -315,23 +315,22 @@ __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsA
 
 // Persistent TMA-fed variant of ls_had_split_kernel (complex64 Y, n_ps == 1, NLTF = 32 or 64): the [NLTF x 64 tones]
 // slab of one (packet, rx, tone tile) is staged into shared memory by ONE cp.async.bulk.tensor.2d per tile
-// (SASS: UTMALDG.2D) through a 2-stage mbarrier ring, issued one tile ahead, so a tile's HBM read is in flight
-// while the previous tile is transformed and emitted (the plain kernel serialises load -> FWHT -> emit per CTA and
-// relies on 9 resident CTAs to cover it).  CTAs walk the tile list with stride gridDim.x: concurrently running CTAs
-// read neighbouring 512-byte segments of the same rows.
-constexpr int kLsTmaStages = 2;
-template <int NLTF>
-constexpr int ls_tma_smem_bytes() { return (kLsTmaStages * NLTF * 64 + NLTF * 68) * 8 + kLsTmaStages * 8 + 128; }
+// (SASS: UTMALDG.2D) through an mbarrier ring of STAGES buffers, issued STAGES-1 tiles ahead, so a tile's HBM read
+// is in flight while the previous tiles are transformed and emitted (the plain kernel serialises load -> FWHT ->
+// emit per CTA and relies on 9 resident CTAs to cover it).  The transform runs IN PLACE in the stage buffer (each
+// thread only rewrites the entries it read), so a stage is also the emit source and no separate work buffer is
+// needed: 32 KB (NLTF 32) / 64 KB (NLTF 64) per CTA with 2 stages.  CTAs walk the tile list with stride gridDim.x:
+// concurrently running CTAs read neighbouring 512-byte segments of the same rows.
+template <int NLTF, int STAGES>
+constexpr int ls_tma_smem_bytes() { return STAGES * NLTF * 64 * 8 + STAGES * 8 + 128; }
 
-template <int S, int NLTF>
+template <int S, int NLTF, int STAGES>
 __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_constant__ CUtensorMap tmap_y, const LsArgs a) {
   constexpr int BLK = 16, NB = NLTF / BLK, T = 64;
   extern __shared__ uint8_t sm_ls_raw[];
   float2* in = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(sm_ls_raw) + 127) & ~static_cast<uintptr_t>(127));
-  float2* sh = in + kLsTmaStages * NLTF * T;             // [NLTF][pitch]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sh + NLTF * (T + 4));
+  uint64_t* full = reinterpret_cast<uint64_t*>(in + STAGES * NLTF * T);
   __shared__ uint32_t cta_abort;
-  const int pitch = T + 4;
   const int n_tiles = (a.n_pil + T - 1) / T;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   auto issue = [&](long long tile, int stage) {
@@ -342,13 +341,13 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
   };
   if (threadIdx.x == 0) {
     cta_abort = 0;
-    for (int s = 0; s < kLsTmaStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_y);
   }
   __syncthreads();
   if (threadIdx.x == 0)
-    for (int s = 0; s < kLsTmaStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       const long long tile = blockIdx.x + static_cast<long long>(s) * gridDim.x;
       if (tile < total) issue(tile, s);
     }
@@ -358,25 +357,23 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
   a2.pil_per_tile = T;
   long long it = 0;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-    const int stage = static_cast<int>(it % kLsTmaStages);
-    const uint32_t parity = static_cast<uint32_t>((it / kLsTmaStages) & 1);
+    const int stage = static_cast<int>(it % STAGES);
+    const uint32_t parity = static_cast<uint32_t>((it / STAGES) & 1);
     const int tl = static_cast<int>(tile % n_tiles);
     const int prx = static_cast<int>(tile / n_tiles);
     const int pil0 = tl * T;
     const int n_here = min(T, a.n_pil - pil0);
     if (!mbar_wait(&full[stage], parity, &cta_abort, a.flags)) return;
-    const float2* src = in + stage * NLTF * T;
-    float2 v[BLK];
+    float2* sh = in + stage * NLTF * T;                  // [NLTF][T], transformed in place
+    {
+      float2 v[BLK];
 #pragma unroll
-    for (int n = 0; n < BLK; ++n) v[n] = src[(b * BLK + n) * T + t];
-    fwht<BLK>(v);
+      for (int n = 0; n < BLK; ++n) v[n] = sh[(b * BLK + n) * T + t];
+      fwht<BLK>(v);
 #pragma unroll
-    for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * pitch + t] = v[j];
-    __syncthreads();                                     // stage fully consumed, sh complete
-    if (threadIdx.x == 0) {
-      const long long next = tile + static_cast<long long>(kLsTmaStages) * gridDim.x;
-      if (next < total) issue(next, stage);
+      for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * T + t] = v[j];
     }
+    __syncthreads();
     if (t < n_here) {
       const float2 inv = __ldg(a.inv_den + pil0 + t);
 #pragma unroll
@@ -384,15 +381,22 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
         const int j = b + jj * NB;
         float2 u[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) u[c] = sh[(c * BLK + j) * pitch + t];
+        for (int c = 0; c < NB; ++c) u[c] = sh[(c * BLK + j) * T + t];
         fwht<NB>(u);
 #pragma unroll
-        for (int c = 0; c < NB; ++c) sh[(c * BLK + j) * pitch + t] = cmul(u[c], inv);
+        for (int c = 0; c < NB; ++c) sh[(c * BLK + j) * T + t] = cmul(u[c], inv);
       }
     }
     __syncthreads();
-    ls_emit<S>(a2, sh, pitch, prx, pil0, pil0);
-    __syncthreads();                                     // sh is rewritten by the next tile
+    ls_emit<S>(a2, sh, T, prx, pil0, pil0);
+    __syncthreads();                                     // stage consumed: refill it for the tile STAGES ahead
+    if (threadIdx.x == 0) {
+      const long long next = tile + static_cast<long long>(STAGES) * gridDim.x;
+      if (next < total) {
+        fence_proxy_async_smem();                        // generic-proxy writes above vs the async-proxy refill
+        issue(next, stage);
+      }
+    }
   }
 }
 

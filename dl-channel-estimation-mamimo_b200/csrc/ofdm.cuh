@@ -230,6 +230,8 @@ template <int R>
 __device__ __forceinline__ void dft_small(float2 (&v)[R]);
 
 template <>
+__device__ __forceinline__ void dft_small<1>(float2 (&)[1]) {}
+template <>
 __device__ __forceinline__ void dft_small<2>(float2 (&v)[2]) {
   const float2 a = v[0], b = v[1];
   v[0] = caddf(a, b);
@@ -264,6 +266,7 @@ struct OfdmR16Args {
   int cp_len, sym_offset, n_sc;
   long long total_syms;
   int x_double;
+  uint32_t* flags;
 };
 
 template <int LOG2N>
@@ -330,6 +333,113 @@ __global__ void __launch_bounds__(256) ofdm_r16_kernel(const OfdmR16Args a) {
       for (int r = 0; r < R3; ++r) {
         const int col = __ldg(a.kmap + jj + 256 * r);
         if (col >= 0) out[col] = w[r];
+      }
+    }
+  }
+}
+
+// Persistent, bulk-copy-fed variant of ofdm_r16_kernel (complex64 input, even cp_len / sym_offset): the FFT windows
+// of the NEXT tile (4096/N symbols) are copied global -> shared by cp.async.bulk (SASS: UBLKCP) while the current
+// tile runs its three passes.  One stage is enough: pass 1 pulls the whole stage into registers at the start of a
+// tile, after which the stage is refilled for the tile gridDim.x ahead.  The cyclic prefix is never read: the copy
+// starts at the window (two copies per symbol when sym_offset < cp_len rotates it).
+template <int LOG2N>
+constexpr int ofdm_r16_tma_smem() { return (1 << LOG2N) * 0 + 4096 * 8 + (4096 + 256) * 8 + 15 * 16 * 8 + 16 + 128; }
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256, 3) ofdm_r16_tma_kernel(const OfdmR16Args a) {
+  constexpr int N = 1 << LOG2N;
+  constexpr int T = N / 16;
+  constexpr int SYMS = 256 / T;
+  constexpr int R3 = N / 256;
+  extern __shared__ uint8_t sm_ofdm_raw[];
+  float2* stage = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(sm_ofdm_raw) + 127) & ~static_cast<uintptr_t>(127));
+  float2 (*buf)[N + N / 16] = reinterpret_cast<float2 (*)[N + N / 16]>(stage + SYMS * N);
+  float2* tw = stage + SYMS * N + SYMS * (N + N / 16);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tw + 15 * 16);
+  __shared__ uint32_t cta_abort;
+  const long long n_tiles = (a.total_syms + SYMS - 1) / SYMS;
+  const int first = N + a.sym_offset - a.cp_len;          // window = x[cp, N+off) ++ x[off, cp)  (dataGenerator.py:442)
+  auto issue = [&](long long tile) {
+    const long long g0 = tile * SYMS;
+    const int live = static_cast<int>(min(static_cast<long long>(SYMS), a.total_syms - g0));
+    mbar_arrive_expect_tx(full, static_cast<uint32_t>(live) * N * 8);
+    const float2* x = reinterpret_cast<const float2*>(a.x);
+    for (int s = 0; s < live; ++s) {
+      const float2* base = x + static_cast<size_t>(g0 + s) * (N + a.cp_len);
+      bulk_load_1d(stage + s * N, base + a.cp_len, static_cast<uint32_t>(first) * 8, full);
+      if (first < N) bulk_load_1d(stage + s * N + first, base + a.sym_offset, static_cast<uint32_t>(N - first) * 8, full);
+    }
+  };
+  if (threadIdx.x == 0) {
+    cta_abort = 0;
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 15 * 16; i += blockDim.x) tw[i] = a.tw2[i];
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) issue(blockIdx.x);
+  const int s = threadIdx.x / T, j = threadIdx.x % T;
+  const int k = j & 15;
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const long long g = tile * SYMS + s;
+    const bool live = g < a.total_syms;
+    if (!mbar_wait(full, it & 1, &cta_abort, a.flags)) return;
+    float2 v[16];
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = stage[s * N + j + T * r];      // pass 1 inputs
+    }
+    __syncthreads();                                       // stage consumed (and last tile's pass 3 is done with buf)
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x);
+    if (live) {
+      dft16(v);                                            // pass 1: ns = 1, output index 16 j + r
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[s][17 * j + r] = v[r];
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = buf[s][pad16(j + T * r)];      // pass 2: ns = 16, k = j mod 16
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = cmulf(v[r], tw[(r - 1) * 16 + k]);
+      dft16(v);
+      if constexpr (R3 == 1) {                             // N = 256: two passes; output bin j + 16 r (k == j)
+        float2* out = a.Y + static_cast<size_t>(g) * a.n_sc;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int col = __ldg(a.kmap + j + 16 * r);
+          if (col >= 0) out[col] = v[r];
+        }
+      } else {
+        const int o = (j - k) * 16 + k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf[s][pad16(o + 16 * r)] = v[r];
+      }
+    }
+    if constexpr (R3 > 1) {
+      __syncthreads();
+      if (live) {
+        float2* out = a.Y + static_cast<size_t>(g) * a.n_sc;
+#pragma unroll
+        for (int b = 0; b < SYMS; ++b) {                   // pass 3: ns = 256, butterfly jj = j + T b
+          const int jj = j + T * b;
+          float2 w[R3];
+#pragma unroll
+          for (int r = 0; r < R3; ++r) w[r] = buf[s][pad16(jj + 256 * r)];
+#pragma unroll
+          for (int r = 1; r < R3; ++r) w[r] = cmulf(w[r], __ldg(a.tw3 + (r - 1) * 256 + jj));
+          dft_small<R3>(w);
+#pragma unroll
+          for (int r = 0; r < R3; ++r) {
+            const int col = __ldg(a.kmap + jj + 256 * r);
+            if (col >= 0) out[col] = w[r];
+          }
+        }
       }
     }
   }
