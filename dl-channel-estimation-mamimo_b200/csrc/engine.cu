@@ -135,6 +135,7 @@ struct mamimo_engine {
   void* lm_in = nullptr;         // host-buffer staging of H_ls / H_mmse chunks
   void* lm_out = nullptr;
   int lm_slabs = 0;
+  bool lm_schur = true;          // Toeplitz (Schur) factorisation; MAMIMO_LMMSE_SCHUR=0: blocked dense Cholesky
   int lm_groups = 4;             // slab groups run on separate streams (MAMIMO_LMMSE_STREAMS; measured 1: 6.81, 2: 6.41, 4: 6.39 ms)
   cudaEvent_t lm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t lm_io_bytes = 0;
@@ -1472,6 +1473,10 @@ mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_ty
     CK(e, cudaMalloc(&e->lm_par, static_cast<size_t>(e->lm_slabs) * sizeof(double2)));
     CK(e, cudaFuncSetAttribute(lmmse_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmPanelSmem));
     CK(e, cudaFuncSetAttribute(lmmse_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
+    CK(e, cudaFuncSetAttribute(lmmse_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
+    if (2 * n_pad * sizeof(double2) > 48 * 1024)
+      CK(e, cudaFuncSetAttribute(lmmse_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(2 * n_pad * sizeof(double2))));
+    if (const char* env = getenv("MAMIMO_LMMSE_SCHUR")) e->lm_schur = atoi(env) != 0;
     for (int i = 0; i < 4; ++i) CK(e, cudaEventCreateWithFlags(&e->lm_ev[i], cudaEventDisableTiming));
     if (const char* env = getenv("MAMIMO_LMMSE_STREAMS")) if (atoi(env) > 0) e->lm_groups = atoi(env);
   }
@@ -1536,6 +1541,28 @@ mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_ty
         b.B = static_cast<const char*>(a.B) + s_lo * slab_el * in_el;
         b.out = static_cast<char*>(a.out) + s_lo * slab_el * out_el;
         b.J = J;
+        if (e->lm_schur) {                     // Toeplitz route: O(n^2) Schur factorisation + blocked triangular solves
+          if (J != nb) continue;
+          {
+            ProfScope ps(e, gst[g], kClsLmmse);
+            lmmse_schur_kernel<<<s_n, 128, 2 * n_pad * sizeof(double2), gst[g]>>>(b);
+          }
+          {
+            ProfScope ps(e, gst[g], kClsLmmse);
+            lmmse_linv_kernel<<<dim3(nb, s_n), 256, 0, gst[g]>>>(b);
+          }
+          {
+            ProfScope ps(e, gst[g], kClsLmmse);
+            lmmse_solve_kernel<<<dim3((nt_pad + 31) / 32, s_n), 128, kLmBsSmem, gst[g]>>>(b);
+          }
+          e->stats.kernel_launches += 3;
+          if (e->cfg.n_ps != 1) {
+            ProfScope ps(e, gst[g], kClsLmmse);
+            lmmse_rhp_kernel<<<dim3((n + 127) / 128, nt, s_n), 128, 0, gst[g]>>>(b);
+            e->stats.kernel_launches++;
+          }
+          continue;
+        }
         if (J < nb) {
           {
             ProfScope ps(e, gst[g], kClsLmmse);

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Measurement of the LMMSE smoother at the reference numerology (32x4, 234 tones) and at the
-bench shape (32x4, 1024 tones): packets/s, FP64 FLOP rate (algorithmic: Cholesky n^3/3 + 2 triangular solves with
-Nt right-hand sides, 8 flops per complex MAC), and the numpy restatement of LMMSE_ce.m on the host beside it.
+bench shape (32x4, 1024 tones): packets/s, FP64 FLOP rate (algorithmic FLOPs of the route in use, see below), and the numpy restatement of LMMSE_ce.m on the host beside it.
 Test infrastructure (imports oracle)."""
 import json
 import os
@@ -58,8 +57,10 @@ for name, nt, nr, nsc, npkt, cpu_pairs in (("ref-numerology 32x4x234", 32, 4, 23
     ref = lmmse.lmmse_batched(H[:1], t_rms[:1], snr[:1])
     err = float(np.linalg.norm(out[:1].cpu().numpy() - ref) / np.linalg.norm(ref))
     n = nsc
-    cmac = n ** 3 / 3.0 + 2 * nt * n * n / 2.0                      # per (pkt, rx) slab
-    flops = 8.0 * cmac * npkt * nr
+    # per (pkt, rx) slab: Toeplitz (Schur) factorisation ~8 n^2 flops + two triangular solves with Nt right-hand
+    # sides (Nt n^2 complex MACs, 8 flops each).  The dense-Cholesky route (MAMIMO_LMMSE_SCHUR=0) needs 8 n^3/3 more.
+    schur = os.environ.get("MAMIMO_LMMSE_SCHUR", "1") != "0"
+    flops = (8.0 * n * n * (nt + 1) if schur else 8.0 * (n ** 3 / 3.0 + nt * n * n)) * npkt * nr
     # CPU: the reference rebuilds + inverts per PAIR (LMMSE_ce.m is called inside the tx loop): time a few pairs
     t0 = time.perf_counter()
     for j in range(cpu_pairs):
@@ -68,7 +69,7 @@ for name, nt, nr, nsc, npkt, cpu_pairs in (("ref-numerology 32x4x234", 32, 4, 23
     print(json.dumps({"case": name, "pkts": npkt, "ms": ms, "packets_per_s": npkt / (ms * 1e-3), "rel_l2_vs_oracle": err,
                       "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": PEAK64, "unit": "TFLOP/s",
                                    "frac": flops / (ms * 1e-3) / 1e12 / PEAK64, "peak_source": "measured cuBLAS DGEMM 4096^3 (this run)",
-                                   "flops": "8 * (n^3/3 + Nt n^2) per (packet, rx), n = Nsc unpadded"},
+                                   "flops": "8 n^2 (Nt + 1) per (packet, rx) [Schur + 2 triangular solves]" if schur else "8 (n^3/3 + Nt n^2) per (packet, rx)"},
                       "launches": prof["lmmse_launches"] // reps,
                       "cpu_numpy_s_per_packet_literal": cpu_pair_s * nt * nr, "cpu_cores": os.cpu_count(),
                       "reference_published_s_per_packet": 1.139 if nsc == 234 else None}), flush=True)
