@@ -35,7 +35,7 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("last_device_flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("last_device_flags", C.c_uint32), ("graph_launches", C.c_uint32)]
 
 
 class Profile(C.Structure):

@@ -139,6 +139,14 @@ struct mamimo_engine {
   int lm_groups = 4;             // slab groups run on separate streams (MAMIMO_LMMSE_STREAMS; measured 1: 6.81, 2: 6.41, 4: 6.39 ms)
   cudaEvent_t lm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t lm_io_bytes = 0;
+  // CUDA-graph cache of the device-resident full path: one graph launch per batch (MAMIMO_GRAPH=0 disables)
+  struct GraphEntry {
+    const void* y; void* hls; float* hr; float* hi; int64_t n_pkt; int y_type; cudaStream_t st;
+    cudaGraphExec_t exec; uint64_t launches; uint64_t stamp;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
+  uint64_t graph_stamp = 0, graph_replays = 0;
   mamimo_stats stats;
   // optional per-kernel-class device timing (mamimo_profile_begin/end)
   struct ProfRec { cudaEvent_t a, b; int cls; };
@@ -160,6 +168,11 @@ mamimo_status fail_cuda(mamimo_engine* e, cudaError_t ce, const char* what) {
     cudaError_t ce_ = (call);                               \
     if (ce_ != cudaSuccess) return fail_cuda(e, ce_, #call); \
   } while (0)
+
+void invalidate_graphs(mamimo_engine* e) {      // any change of tables / weights / workspace pointers
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
 
 enum { kClsLs = 0, kClsFc = 1, kClsStage = 2, kClsLmmse = 3 };   // the OFDM demod kernel is booked under kClsStage
 // RAII event bracket around one launch (no-op unless profiling)
@@ -908,6 +921,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA_STAGES")) e->ls_tma_stages = atoi(env) == 3 ? 3 : 2;
@@ -985,6 +999,7 @@ void mamimo_destroy(mamimo_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
+  invalidate_graphs(e);
   if (e->d_dbg) {          // diagnostic dump: average cycles per cluster over the engine's lifetime
     unsigned long long h[8] = {0};
     cudaMemcpy(h, e->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1019,6 +1034,7 @@ void mamimo_destroy(mamimo_engine* e) {
 
 mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P) {
   if (!e) return MAMIMO_ERR_INVALID;
+  invalidate_graphs(e);
   CK(e, cudaSetDevice(e->cfg.device));
   const int nt = e->cfg.n_tx, nl = e->cfg.n_ltf;
   e->hP.assign(static_cast<size_t>(2) * nt * nl, 0.f);
@@ -1071,6 +1087,7 @@ mamimo_status mamimo_load_layer(mamimo_engine* e, int32_t net, int32_t layer, co
 
 mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
   if (!e) return MAMIMO_ERR_INVALID;
+  invalidate_graphs(e);
   if (e->n_layers == 0) return fail(e, MAMIMO_ERR_STATE, "no MLP configured");
   CK(e, cudaSetDevice(e->cfg.device));
   for (int net = 0; net < 2; ++net)
@@ -1205,6 +1222,47 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
     }
     return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, nets, gather)));
   };
+  // Device-resident full path on a capturable stream: the 7 launches of a batch are captured once per
+  // (buffers, batch size, stream) and replayed as ONE graph launch afterwards.
+  cudaStream_t ust = static_cast<cudaStream_t>(stream);
+  if (mem == MAMIMO_MEM_DEVICE && stages == all && !gather && e->use_graphs && !e->profiling && ust != nullptr &&
+      ust != cudaStreamLegacy && ust != cudaStreamPerThread && n_pkt > 0) {
+    cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ust, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone) {
+      for (auto& g : e->graphs)
+        if (g.y == Y && g.hls == H_ls && g.hr == H_real && g.hi == H_imag && g.n_pkt == n_pkt &&
+            g.y_type == static_cast<int>(y_type) && g.st == ust) {
+          g.stamp = ++e->graph_stamp;
+          CK(e, cudaGraphLaunch(g.exec, ust));
+          e->stats.kernel_launches += g.launches;
+          e->graph_replays++;
+          e->stats.graph_launches++;
+          return MAMIMO_OK;
+        }
+      const uint64_t l0 = e->stats.kernel_launches;
+      CK(e, cudaStreamBeginCapture(ust, cudaStreamCaptureModeRelaxed));
+      const mamimo_status cs = run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem, ust, stage);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(ust, &graph);
+      if (cs != MAMIMO_OK) { if (graph) cudaGraphDestroy(graph); return cs; }
+      if (ce != cudaSuccess) return fail_cuda(e, ce, "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ci != cudaSuccess) return fail_cuda(e, ci, "cudaGraphInstantiate");
+      if (e->graphs.size() >= 8) {                       // evict the least recently used entry
+        size_t lru = 0;
+        for (size_t i = 1; i < e->graphs.size(); ++i) if (e->graphs[i].stamp < e->graphs[lru].stamp) lru = i;
+        cudaGraphExecDestroy(e->graphs[lru].exec);
+        e->graphs.erase(e->graphs.begin() + lru);
+      }
+      e->graphs.push_back({Y, H_ls, H_real, H_imag, n_pkt, static_cast<int>(y_type), ust, exec,
+                           e->stats.kernel_launches - l0, ++e->graph_stamp});
+      CK(e, cudaGraphLaunch(exec, ust));
+      e->stats.graph_launches++;
+      return MAMIMO_OK;
+    }
+  }
   return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hlsb, H_real, H_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
 }

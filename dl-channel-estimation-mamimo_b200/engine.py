@@ -369,7 +369,7 @@ class Engine:
         s = _capi.Stats()
         check(lib.mamimo_get_stats(self._h, C.byref(s)), self._h)
         return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes), d2h_bytes=int(s.d2h_bytes),
-                    last_device_flags=int(s.last_device_flags))
+                    last_device_flags=int(s.last_device_flags), graph_launches=int(s.graph_launches))
 
 
 def ipc_export(dev_ptr):

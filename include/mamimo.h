@@ -102,7 +102,8 @@ typedef struct {
   uint64_t h2d_bytes;         /* bytes copied host->device by the engine */
   uint64_t d2h_bytes;
   uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout, bit2 LMMSE matrix not positive definite */
-  uint32_t reserved;
+  uint32_t graph_launches;    /* device-resident full-path calls issued as ONE CUDA-graph launch (captured once per
+                                 (buffers, batch size, stream), replayed afterwards; MAMIMO_GRAPH=0 disables) */
 } mamimo_stats;
 
 /* device time per kernel class, measured with CUDA events recorded on the launching stream */
@@ -159,7 +160,8 @@ MAMIMO_API mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mam
 /* Full path, mode C: Y -> LS -> interp -> two FC nets.  H_ls may be NULL.  mem applies to Y, H_ls,
  * H_real, H_imag alike.  Host buffers are streamed through the device in chunks of max_pkts with
  * copies overlapped with compute.  Synchronous w.r.t. the host when mem == HOST; asynchronous on
- * `stream` when mem == DEVICE. */
+ * `stream` when mem == DEVICE.  On a non-default stream the device-resident call is captured into a CUDA graph the
+ * first time it is seen with given buffers / batch size and replayed as ONE graph launch afterwards. */
 MAMIMO_API mamimo_status mamimo_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y_type,
                                          int64_t n_pkt, void* H_ls, float* H_real, float* H_imag,
                                          mamimo_mem mem, void* stream);

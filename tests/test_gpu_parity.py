@@ -503,3 +503,40 @@ def test_mode_a_reference_literal_shapes(precision):
         ref = mlp.forward(np.concatenate([xsig, xp], axis=1), nets[name])
         assert Y.shape == (2 * nr * nt, d_out)
         assert rel_l2(ref, Y) <= TOL_DNN, name
+
+
+def test_device_path_replays_as_one_cuda_graph():
+    """On a non-default stream the device-resident call is captured once and replayed as ONE graph launch; the result is
+    bitwise identical to the plainly launched path (default stream), and new buffers / batch sizes re-capture."""
+    import torch
+    nt, nr, nsc, npkt, hidden = 32, 2, 128, 6, (128, 64)
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    Y, _ = mm.synth.make_packets(23, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    Yd = torch.from_numpy(Y).cuda()
+    with mm.Engine(nt, nr, nsc, hidden=hidden, precision="fp16x3") as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr0, Hi0 = eng.estimate(Yd)                                   # default stream: plain launches
+        torch.cuda.synchronize()
+        assert eng.stats()["graph_launches"] == 0
+        st = torch.cuda.Stream()
+        rows = npkt * nt * nr
+        Hr = torch.zeros((rows, nsc), dtype=torch.float32, device="cuda")
+        Hi = torch.zeros_like(Hr)
+        torch.cuda.synchronize()
+        l0 = eng.stats()["kernel_launches"]
+        for _ in range(3):
+            eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, st.cuda_stream)
+        st.synchronize()
+        s1 = eng.stats()
+        assert s1["graph_launches"] == 3 and s1["kernel_launches"] - l0 == 3 * 7
+        assert torch.equal(Hr, Hr0) and torch.equal(Hi, Hi0)
+        Hr.zero_()
+        eng.estimate_raw(Yd.data_ptr(), 0, npkt - 2, 0, Hr.data_ptr(), Hi.data_ptr(), 1, st.cuda_stream)   # other batch size
+        st.synchronize()
+        assert torch.equal(Hr[: (npkt - 2) * nt * nr], Hr0[: (npkt - 2) * nt * nr]) and not Hr[(npkt - 2) * nt * nr:].any()
+        eng.set_pilots(x, None)                                       # invalidates the cache; still correct afterwards
+        eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, st.cuda_stream)
+        st.synchronize()
+        assert torch.equal(Hr, Hr0)
