@@ -8,6 +8,9 @@
 //   [hD, Hr, Hi] = mamimo_mex('estimate', rxData)  Hr/Hi single [Nsc x Nt*Nr*Npkt] (column = pair row)
 //   hM = mamimo_mex('lmmse', hD, tau, SNR)         LMMSE_ce over all pairs: tau = the `h` vector of LMMSE_ce (one per call)
 //                                                  or a [Ntau x Npkt] matrix, SNR(i) in dB [Nr (x Npkt)]
+//   mamimo_mex('ofdm', fftLen, cpLen, symOffset, carriers)   ofdmdemod parameters; carriers = prm.CarriersLocations
+//   Y = mamimo_mex('demod', x)                     x complex double [nltf*(fftLen+cpLen) x Nr (x Npkt)] (inputRXSig) ->
+//                                                  Y complex single [Nsc x nltf x Nr (x Npkt)] (= rxOFDM(:,1:nltf,:))
 //   ltf = mamimo_mex('ltf')                        256 x 1 tone table (no engine needed)
 //   mamimo_mex('destroy')
 //
@@ -52,6 +55,7 @@ static mwSize check_rx(const mxArray* rx, const mamimo_config* c) {
 }
 
 static mamimo_config g_cfg;
+static int g_fft = 0, g_cp = 0;
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("mamimo:usage", "first argument must be a command string");
@@ -133,6 +137,26 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       fail(mamimo_estimate(g_engine, mxGetComplexDoubles(prhs[1]), MAMIMO_C128, (int64_t)np, NULL,
                            mxGetSingles(plhs[1]), mxGetSingles(plhs[2]), MAMIMO_MEM_HOST, NULL));
     }
+  } else if (!strcmp(cmd, "ofdm")) {             // ofdmdemod(x, FFT, CP, symOffset, null, pilot), pg/generate_maMIMO_LTF.m:336-338
+    need_engine();
+    if (nrhs < 5 || !mxIsDouble(prhs[4])) mexErrMsgIdAndTxt("mamimo:usage", "mamimo_mex('ofdm', fftLen, cpLen, symOffset, carriers)");
+    if (mxGetNumberOfElements(prhs[4]) != (size_t)g_cfg.n_sc) mexErrMsgIdAndTxt("mamimo:size", "need Nsc carrier indices");
+    static int32_t car[65536];
+    for (int i = 0; i < g_cfg.n_sc; ++i) car[i] = (int32_t)mxGetDoubles(prhs[4])[i];
+    g_fft = (int)mxGetScalar(prhs[1]); g_cp = (int)mxGetScalar(prhs[2]);
+    fail(mamimo_set_ofdm(g_engine, g_fft, g_cp, (int)mxGetScalar(prhs[3]), car));
+  } else if (!strcmp(cmd, "demod")) {
+    need_engine();
+    if (nrhs < 2 || !mxIsComplex(prhs[1]) || !mxIsDouble(prhs[1])) mexErrMsgIdAndTxt("mamimo:type", "x must be complex double");
+    const mwSize nd = mxGetNumberOfDimensions(prhs[1]);
+    const mwSize* d = mxGetDimensions(prhs[1]);
+    const mwSize nr = nd >= 2 ? d[1] : 1, np = nd >= 3 ? d[2] : 1;
+    if (g_fft == 0 || d[0] != (mwSize)g_cfg.n_ltf * (g_fft + g_cp) || nr != (mwSize)g_cfg.n_rx)
+      mexErrMsgIdAndTxt("mamimo:size", "x must be [nltf*(fftLen+cpLen) x Nr (x Npkt)]; call mamimo_mex('ofdm', ...) first");
+    const mwSize od[4] = {(mwSize)g_cfg.n_sc, (mwSize)g_cfg.n_ltf, (mwSize)g_cfg.n_rx, np};
+    plhs[0] = mxCreateNumericArray(np > 1 ? 4 : 3, od, mxSINGLE_CLASS, mxCOMPLEX);
+    fail(mamimo_ofdm_demod(g_engine, mxGetComplexDoubles(prhs[1]), MAMIMO_C128, (int64_t)np, mxGetComplexSingles(plhs[0]),
+                           MAMIMO_MEM_HOST, NULL));
   } else if (!strcmp(cmd, "lmmse")) {            // isMMSE branch of pg/helperMIMOChannelEstimate.m:37-39
     need_engine();
     if (nrhs < 4) mexErrMsgIdAndTxt("mamimo:usage", "hM = mamimo_mex('lmmse', hD, tau, SNR)");

@@ -12,6 +12,7 @@ extern "C" {
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef struct { double real, imag; } mxComplexDouble;
+typedef struct { float real, imag; } mxComplexSingle;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 typedef enum { mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7 } mxClassID;
 mwSize mxGetNumberOfDimensions(const mxArray*);
@@ -30,6 +31,7 @@ char* mxArrayToString(const mxArray*);
 void mxFree(void*);
 mxArray* mxGetField(const mxArray*, mwSize, const char*);
 mxComplexDouble* mxGetComplexDoubles(const mxArray*);
+mxComplexSingle* mxGetComplexSingles(const mxArray*);
 double* mxGetDoubles(const mxArray*);
 float* mxGetSingles(const mxArray*);
 mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
