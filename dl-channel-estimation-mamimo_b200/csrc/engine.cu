@@ -73,7 +73,6 @@ struct mamimo_engine {
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
   bool ofdm_tma = true;         // persistent bulk-copy-fed OFDM kernel (MAMIMO_OFDM_TMA=0: plain three-pass kernel)
   bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
-  int ls_tma_stages = 2;        // stage buffers per CTA (MAMIMO_LS_TMA_STAGES = 2 | 3)
   int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
   int ls_tile = 64;             // tones per CTA of the split LS kernel (MAMIMO_LS_TILE=128: experiment)
   bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
@@ -311,32 +310,32 @@ mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st
 }
 
 // TMA-fed persistent LS kernel: per-call tensor map over Y viewed as float32 [n_pkt*n_rx*n_ltf][2*n_sc]
-template <int S, int NLTF, int STAGES>
+template <int S, int NLTF, int STAGES, int NPS>
 mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   CUtensorMap map;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2) * a.n_sc, static_cast<cuuint64_t>(a.n_pkt) * a.n_rx * a.n_ltf};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.n_sc) * 8};
-  const cuuint32_t box[2] = {128, static_cast<cuuint32_t>(NLTF)};
+  const cuuint32_t box[2] = {2u * ls_tma_row_tones<NPS>(), static_cast<cuuint32_t>(NLTF)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(a.Y), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (LS) failed: " + std::to_string(r));
-  constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES>();
+  constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES, NPS>();
   static bool attr_set = false;
   if (!attr_set) {
-    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int n_tiles = (a.n_pil + 63) / 64;
+  const int n_tiles = (a.n_sc + 63) / 64;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   const int per_sm = std::max(1, std::min(e->ls_tma_ctas, (227 * 1024) / (smem + 1024)));
   const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(e->num_sms) * per_sm));
   {
     ProfScope ps(e, st, kClsLs);
-    ls_tma_kernel<S, NLTF, STAGES><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
+    ls_tma_kernel<S, NLTF, STAGES, NPS><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
   }
   CK(e, cudaGetLastError());
   e->stats.kernel_launches++;
@@ -345,9 +344,16 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
 
 template <int S>
 mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
-  if (e->hadamard && a.n_ps == 1 && e->ls_split && e->ls_tma && !a.y_double && (a.n_sc % 2) == 0) {
-    if (a.n_ltf == 32) return e->ls_tma_stages == 3 ? launch_ls_tma<S, 32, 3>(e, a, st) : launch_ls_tma<S, 32, 2>(e, a, st);
-    if (a.n_ltf == 64) return e->ls_tma_stages == 3 ? launch_ls_tma<S, 64, 3>(e, a, st) : launch_ls_tma<S, 64, 2>(e, a, st);
+  if (e->hadamard && e->ls_split && e->ls_tma && !a.y_double && (a.n_sc % 2) == 0 && (a.n_ltf == 32 || a.n_ltf == 64)) {
+    // persistent TMA-fed kernel; comb pilots (n_ps = 2, 4, 8) interpolate in its emit phase
+    const bool comb_ok = (a.n_sc % 64) == 0 && (a.kpad & 3) == 0 && a.n_pil >= 2;
+#define LS_TMA_CASE(NPS)                                                                        \
+  return a.n_ltf == 32 ? launch_ls_tma<S, 32, 2, NPS>(e, a, st) : launch_ls_tma<S, 64, 2, NPS>(e, a, st);
+    if (a.n_ps == 1) { LS_TMA_CASE(1) }
+    if (comb_ok && a.n_ps == 2) { LS_TMA_CASE(2) }
+    if (comb_ok && a.n_ps == 4) { LS_TMA_CASE(4) }
+    if (comb_ok && a.n_ps == 8) { LS_TMA_CASE(8) }
+#undef LS_TMA_CASE
   }
   // every reference call site (n_ps = 1, Hadamard P, 32 or 64 antennas): transform split over threads
   if (e->hadamard && a.n_ps == 1 && e->ls_split) {
@@ -924,7 +930,6 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
-  if (const char* env = getenv("MAMIMO_LS_TMA_STAGES")) e->ls_tma_stages = atoi(env) == 3 ? 3 : 2;
   if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;
   if (const char* env = getenv("MAMIMO_FC_DEBUG")) {

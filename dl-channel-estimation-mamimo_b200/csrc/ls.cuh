@@ -62,6 +62,64 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// 4 consecutive tones (k .. k+3) of pair row `row`: optional H_ls plus the split operand planes of both nets,
+// 8/16/32-byte stores
+template <int S>
+__device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, const float (&re)[4], const float (&im)[4],
+                                          bool& ovf) {
+  using Sch = Scheme<S>;
+  using E = typename Sch::elem;
+  if (a.H_ls) {
+    if (a.h_double) {
+      double2* d = reinterpret_cast<double2*>(a.H_ls) + row * a.n_sc + k;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = make_double2(re[i], im[i]);
+    } else {
+      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.H_ls) + row * a.n_sc + k);
+      d[0] = make_float4(re[0], im[0], re[1], im[1]);
+      d[1] = make_float4(re[2], im[2], re[3], im[3]);
+    }
+  }
+  if (a.planes[0]) {
+    if constexpr (S == kFp16x3) {
+      uint32_t r01[2], r23[2], i01[2], i23[2];
+      Sch::split2(re[0], re[1], a.scale, r01, &ovf);
+      Sch::split2(re[2], re[3], a.scale, r23, &ovf);
+      Sch::split2(im[0], im[1], a.scale, i01, &ovf);
+      Sch::split2(im[2], im[3], a.scale, i23, &ovf);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+        *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[0]) + off) = make_uint2(r01[pl], r23[pl]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[1]) + off) = make_uint2(i01[pl], i23[pl]);
+      }
+    } else {
+      E pr[4][Sch::kPlanes], pi[4][Sch::kPlanes];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        Sch::split(re[i], a.scale, pr[i], &ovf);
+        Sch::split(im[i], a.scale, pi[i], &ovf);
+      }
+#pragma unroll
+      for (int pl = 0; pl < Sch::kPlanes; ++pl) {
+        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+        E* d0 = reinterpret_cast<E*>(a.planes[0]) + off;
+        E* d1 = reinterpret_cast<E*>(a.planes[1]) + off;
+        if constexpr (sizeof(E) == 4) {
+          *reinterpret_cast<float4*>(d0) = make_float4(pr[0][pl], pr[1][pl], pr[2][pl], pr[3][pl]);
+          *reinterpret_cast<float4*>(d1) = make_float4(pi[0][pl], pi[1][pl], pi[2][pl], pi[3][pl]);
+        } else {
+          auto bits = [](E x) { return static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&x)); };
+          *reinterpret_cast<uint2*>(d0) = make_uint2(bits(pr[0][pl]) | (bits(pr[1][pl]) << 16),
+                                                     bits(pr[2][pl]) | (bits(pr[3][pl]) << 16));
+          *reinterpret_cast<uint2*>(d1) = make_uint2(bits(pi[0][pl]) | (bits(pi[1][pl]) << 16),
+                                                     bits(pi[2][pl]) | (bits(pi[3][pl]) << 16));
+        }
+      }
+    }
+  }
+}
+
 // Phase 2 of the LS kernels: the CTA sweeps (tx, k) of its tile with k fastest, interpolates between pilots when
 // n_ps > 1 (n_ps == 1 is a pure copy: bit-exact identity) and writes H_ls and the split operand planes.
 template <int S>
@@ -86,57 +144,7 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
       const float4 v23 = *reinterpret_cast<const float4*>(sh + j * pitch + kk + 2);
       const float re[4] = {v01.x, v01.z, v23.x, v23.z};
       const float im[4] = {v01.y, v01.w, v23.y, v23.w};
-      const size_t row = row0 + j;
-      const int k = k0 + kk;
-      if (a.H_ls) {
-        if (a.h_double) {
-          double2* d = reinterpret_cast<double2*>(a.H_ls) + row * a.n_sc + k;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) d[i] = make_double2(re[i], im[i]);
-        } else {
-          float4* d = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.H_ls) + row * a.n_sc + k);
-          d[0] = v01;
-          d[1] = v23;
-        }
-      }
-      if (a.planes[0]) {
-        if constexpr (S == kFp16x3) {
-          uint32_t r01[2], r23[2], i01[2], i23[2];
-          Sch::split2(re[0], re[1], a.scale, r01, &ovf);
-          Sch::split2(re[2], re[3], a.scale, r23, &ovf);
-          Sch::split2(im[0], im[1], a.scale, i01, &ovf);
-          Sch::split2(im[2], im[3], a.scale, i23, &ovf);
-#pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
-            const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
-            *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[0]) + off) = make_uint2(r01[pl], r23[pl]);
-            *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[1]) + off) = make_uint2(i01[pl], i23[pl]);
-          }
-        } else {
-        E pr[4][Sch::kPlanes], pi[4][Sch::kPlanes];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          Sch::split(re[i], a.scale, pr[i], &ovf);
-          Sch::split(im[i], a.scale, pi[i], &ovf);
-        }
-#pragma unroll
-        for (int pl = 0; pl < Sch::kPlanes; ++pl) {
-          const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
-          E* d0 = reinterpret_cast<E*>(a.planes[0]) + off;
-          E* d1 = reinterpret_cast<E*>(a.planes[1]) + off;
-          if constexpr (sizeof(E) == 4) {
-            *reinterpret_cast<float4*>(d0) = make_float4(pr[0][pl], pr[1][pl], pr[2][pl], pr[3][pl]);
-            *reinterpret_cast<float4*>(d1) = make_float4(pi[0][pl], pi[1][pl], pi[2][pl], pi[3][pl]);
-          } else {
-            auto bits = [](E x) { return static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&x)); };
-            *reinterpret_cast<uint2*>(d0) = make_uint2(bits(pr[0][pl]) | (bits(pr[1][pl]) << 16),
-                                                       bits(pr[2][pl]) | (bits(pr[3][pl]) << 16));
-            *reinterpret_cast<uint2*>(d1) = make_uint2(bits(pi[0][pl]) | (bits(pi[1][pl]) << 16),
-                                                       bits(pi[2][pl]) | (bits(pi[3][pl]) << 16));
-          }
-        }
-        }
-      }
+      ls_store4<S>(a, row0 + j, k0 + kk, re, im, ovf);
     }
   } else {
     const float inv_nps = 1.0f / static_cast<float>(a.n_ps);
@@ -321,23 +329,28 @@ __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsA
 // thread only rewrites the entries it read), so a stage is also the emit source and no separate work buffer is
 // needed: 32 KB (NLTF 32) / 64 KB (NLTF 64) per CTA with 2 stages.  CTAs walk the tile list with stride gridDim.x:
 // concurrently running CTAs read neighbouring 512-byte segments of the same rows.
-template <int NLTF, int STAGES>
-constexpr int ls_tma_smem_bytes() { return STAGES * NLTF * 64 * 8 + STAGES * 8 + 128; }
+// NPS > 1 (comb pilots, the north_star's interpolation stage): the stage rows hold 72 tones, i.e. the tile plus the
+// halo pilot the last segment interpolates towards; only the pilot columns are despread (in place), and the emit
+// phase interpolates linearly between neighbouring pilots (same arithmetic as the generic kernel / oracle.interp).
+template <int NPS>
+__host__ __device__ constexpr int ls_tma_row_tones() { return NPS == 1 ? 64 : 72; }
+template <int NLTF, int STAGES, int NPS>
+constexpr int ls_tma_smem_bytes() { return STAGES * NLTF * ls_tma_row_tones<NPS>() * 8 + STAGES * 8 + 128; }
 
-template <int S, int NLTF, int STAGES>
+template <int S, int NLTF, int STAGES, int NPS>
 __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_constant__ CUtensorMap tmap_y, const LsArgs a) {
-  constexpr int BLK = 16, NB = NLTF / BLK, T = 64;
+  constexpr int BLK = 16, NB = NLTF / BLK, T = 64, TW = ls_tma_row_tones<NPS>(), PT = T / NPS;
   extern __shared__ uint8_t sm_ls_raw[];
   float2* in = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(sm_ls_raw) + 127) & ~static_cast<uintptr_t>(127));
-  uint64_t* full = reinterpret_cast<uint64_t*>(in + STAGES * NLTF * T);
+  uint64_t* full = reinterpret_cast<uint64_t*>(in + STAGES * NLTF * TW);
   __shared__ uint32_t cta_abort;
-  const int n_tiles = (a.n_pil + T - 1) / T;
+  const int n_tiles = (a.n_sc + T - 1) / T;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   auto issue = [&](long long tile, int stage) {
     const int tl = static_cast<int>(tile % n_tiles);
     const long long prx = tile / n_tiles;
-    mbar_arrive_expect_tx(&full[stage], NLTF * T * 8);
-    tma_load_2d(in + stage * NLTF * T, &tmap_y, &full[stage], tl * T * 2, static_cast<int32_t>(prx * NLTF));
+    mbar_arrive_expect_tx(&full[stage], NLTF * TW * 8);
+    tma_load_2d(in + stage * NLTF * TW, &tmap_y, &full[stage], tl * T * 2, static_cast<int32_t>(prx * NLTF));
   };
   if (threadIdx.x == 0) {
     cta_abort = 0;
@@ -361,34 +374,61 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
     const uint32_t parity = static_cast<uint32_t>((it / STAGES) & 1);
     const int tl = static_cast<int>(tile % n_tiles);
     const int prx = static_cast<int>(tile / n_tiles);
-    const int pil0 = tl * T;
-    const int n_here = min(T, a.n_pil - pil0);
+    const int pil0 = tl * PT;                            // first pilot of the tile
+    // pilots this thread column handles: NPS == 1 every tone of the tile; else PT pilots + the halo pilot
+    const bool active = NPS == 1 ? (t < min(T, a.n_pil - pil0)) : (t <= PT && pil0 + t < a.n_pil);
+    const int col = t * NPS;
     if (!mbar_wait(&full[stage], parity, &cta_abort, a.flags)) return;
-    float2* sh = in + stage * NLTF * T;                  // [NLTF][T], transformed in place
-    {
+    float2* sh = in + stage * NLTF * TW;                 // [NLTF][TW], transformed in place
+    if (NPS == 1 || active) {
       float2 v[BLK];
 #pragma unroll
-      for (int n = 0; n < BLK; ++n) v[n] = sh[(b * BLK + n) * T + t];
+      for (int n = 0; n < BLK; ++n) v[n] = sh[(b * BLK + n) * TW + col];
       fwht<BLK>(v);
 #pragma unroll
-      for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * T + t] = v[j];
+      for (int j = 0; j < BLK; ++j) sh[(b * BLK + j) * TW + col] = v[j];
     }
     __syncthreads();
-    if (t < n_here) {
+    if (active) {
       const float2 inv = __ldg(a.inv_den + pil0 + t);
 #pragma unroll
       for (int jj = 0; jj < BLK / NB; ++jj) {
         const int j = b + jj * NB;
         float2 u[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) u[c] = sh[(c * BLK + j) * T + t];
+        for (int c = 0; c < NB; ++c) u[c] = sh[(c * BLK + j) * TW + col];
         fwht<NB>(u);
 #pragma unroll
-        for (int c = 0; c < NB; ++c) sh[(c * BLK + j) * T + t] = cmul(u[c], inv);
+        for (int c = 0; c < NB; ++c) sh[(c * BLK + j) * TW + col] = cmul(u[c], inv);
       }
     }
     __syncthreads();
-    ls_emit<S>(a2, sh, T, prx, pil0, pil0);
+    if constexpr (NPS == 1) {
+      ls_emit<S>(a2, sh, TW, prx, pil0, pil0);
+    } else {
+      const int k0 = tl * T;
+      const int nk = min(T, a.n_sc - k0);
+      const float inv_nps = 1.0f / static_cast<float>(NPS);
+      const size_t row0 = static_cast<size_t>(prx) * a.n_tx;
+      bool ovf = false;
+      for (int idx = threadIdx.x; idx < a.n_tx * (T / 4); idx += blockDim.x) {
+        const int j = idx >> 4, kk = (idx & 15) << 2;
+        if (kk >= nk) continue;
+        float re[4], im[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = k0 + kk + i;
+          const int seg = min(k / NPS, a.n_pil - 2);
+          const float w = static_cast<float>(k - seg * NPS) * inv_nps;
+          const float2 h0 = sh[j * TW + (seg * NPS - k0)];
+          const float2 h1 = sh[j * TW + (seg * NPS - k0) + NPS];
+          re[i] = h0.x + w * (h1.x - h0.x);
+          im[i] = h0.y + w * (h1.y - h0.y);
+        }
+        ls_store4<S>(a, row0 + j, k0 + kk, re, im, ovf);
+      }
+      if (ovf) atomicOr(a.flags, kFlagRange);
+    }
     __syncthreads();                                     // stage consumed: refill it for the tile STAGES ahead
     if (threadIdx.x == 0) {
       const long long next = tile + static_cast<long long>(STAGES) * gridDim.x;

@@ -80,6 +80,26 @@ def test_ls_interp_parity(nps, nsc):
     assert rel_l2(oracle_ls(Y, tables.sylvester_hadamard(nt), xp, nps), H) <= TOL_LS
 
 
+@pytest.mark.parametrize("nt,nr,nps,nsc", [(32, 2, 2, 256), (32, 2, 4, 1024), (32, 1, 8, 192), (64, 2, 4, 128), (64, 1, 2, 2048)])
+def test_ls_interp_parity_tma_kernel(nt, nr, nps, nsc, monkeypatch):
+    """32/64 antennas with comb pilots take the persistent TMA-fed kernel (halo pilot per tile, interpolation in the
+    emit phase); it must agree with the oracle and, bitwise, with the generic kernel (MAMIMO_LS_TMA=0)."""
+    npkt = 3
+    xp = mm.synth.make_pilots(nsc, nps)
+    x_full = np.ones(nsc)
+    x_full[::nps] = xp
+    Y, _ = mm.synth.make_packets(24, npkt, nt, nr, nsc, snr_db=20.0, x_tones=x_full)
+    with mm.Engine(nt, nr, nsc, n_ps=nps, mlp=False) as eng:
+        eng.set_pilots(xp, None)
+        H = eng.ls_estimate(Y)
+    assert rel_l2(oracle_ls(Y, tables.sylvester_hadamard(nt), xp, nps), H) <= TOL_LS
+    monkeypatch.setenv("MAMIMO_LS_TMA", "0")
+    with mm.Engine(nt, nr, nsc, n_ps=nps, mlp=False) as eng:
+        eng.set_pilots(xp, None)
+        H0 = eng.ls_estimate(Y)
+    assert rel_l2(H0.astype(np.complex128), H) <= 2e-7       # same formula; FMA contraction may differ by an ulp
+
+
 def test_ls_linearity_property():
     nt, nr, nsc, npkt = 32, 4, 1024, 4
     x = mm.synth.make_pilots(nsc)
