@@ -15,12 +15,14 @@ Pinning status (see DESIGN.md "Oracle"):
   (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
 * ``oracle.tables`` (VHT-LTF tone table, carrier index set) is pinned by the
   integer known-answers listed in SURVEY.md section 8(a2)/(c).
-* ``oracle.ls`` (helperMIMOChannelEstimate) and ``oracle.mlp`` (Keras FC
-  graph) restate MATLAB / TensorFlow code that cannot run here (no MATLAB,
-  Octave, TensorFlow, h5py): **parity unpinned** by execution of the
-  reference; they are anchored on algebraic known-answer identities only.
-* ``oracle.lmmse`` (LMMSE_ce.m via helperMIMOChannelEstimate.m:37-39) restates MATLAB code: **parity
-  unpinned** by execution; anchored on the identities listed in its header.
+* ``oracle.ls`` (helperMIMOChannelEstimate.m) and ``oracle.lmmse`` (LMMSE_ce.m and its call site) are PINNED
+  against the reference's own MATLAB source text, executed unmodified by the MATLAB-subset interpreter
+  ``tests/golden/mini_matlab.py`` (MATLAB / Octave are not installed): ``tests/golden/ref_matlab_ls_lmmse.npz``,
+  checked in ``tests/test_golden_matlab.py`` (LS 1e-16, LMMSE 1e-12 incl. per-rx SNR, Nps = 2 and the data-phase
+  numSTS = 1 case).  ``helperGetP`` (a MathWorks example helper, not in the reference repo) is input data there.
+* ``oracle.mlp`` (Keras FC graph) restates TensorFlow layer semantics that cannot run here (no TensorFlow / h5py):
+  **parity unpinned** by execution of TensorFlow itself; the glue around it (``CSIPredictor.inference`` end to end
+  with a numpy Keras stand-in) is pinned, and the layer arithmetic is anchored on BN-fold == unfused identities.
 * ``oracle.interp`` has no reference counterpart at all (the reference always
   uses Nps = 1): **parity unpinned**, defined here.
 """

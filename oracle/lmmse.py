@@ -21,7 +21,10 @@ and the caller, packet_generation/phased_arr/helperMIMOChannelEstimate.m:37-39:
 scattering channel); LMMSE_ce only uses it through tau_rms, so the engine's API takes tau_rms per packet
 (`tau_rms()` below is the restated formula) and SNR in dB per (packet, rx).
 
-Parity unpinned by execution (no MATLAB/Octave here).  Anchors (tests/test_oracle.py): the literal form equals
+PINNED: tests/golden/ref_matlab_ls_lmmse.npz holds the outputs of the reference's own LMMSE_ce.m /
+helperMIMOChannelEstimate.m source text, executed unmodified by tests/golden/mini_matlab.py (MATLAB / Octave are
+not installed); tests/test_golden_matlab.py checks this module against them to 1e-12 (per-rx SNR, Nps = 2,
+delays in seconds).  Further anchors (tests/test_lmmse_oracle.py): the literal form equals
 the solve form; Rpp is Hermitian positive definite; tau_rms of a two-tap profile has the closed form; with
 Nps = 1 the result equals H - (1/snr) * inv(Rpp) * H; snr -> inf gives the identity to ~1e-6.
 """

@@ -13,8 +13,10 @@ MATLAB arrays are column-major, so rxData [Nsc x nltf x Nr] has memory order
 batched forms below use exactly those C-order layouts with a leading packet
 axis: Y[pkt, rx, sym, k] -> H[pkt, rx, tx, k].
 
-Parity unpinned by execution (no MATLAB/Octave here); anchored by the
-round-trip identity of SURVEY.md 8(c)(ii) in tests/test_oracle.py.
+PINNED: tests/golden/ref_matlab_ls_lmmse.npz holds the outputs of the reference's own
+helperMIMOChannelEstimate.m source text, executed unmodified by tests/golden/mini_matlab.py
+(MATLAB / Octave are not installed); tests/test_golden_matlab.py checks this module against
+them to 1e-15.  Also anchored by the round-trip identity of SURVEY.md 8(c)(ii) in tests/test_oracle.py.
 """
 import numpy as np
 

@@ -9,6 +9,11 @@ What is pinned here:
   2. inference.py's CSIPredictor.inference() executed unmodified, with a stub
      ``tensorflow.keras`` whose load_model() returns a deterministic numpy MLP
      (TensorFlow itself is not installed).  Pins pre/post-processing glue.
+  4. helperMIMOChannelEstimate.m and LMMSE_ce.m (MATLAB) executed UNMODIFIED by the MATLAB-subset interpreter
+     tests/golden/mini_matlab.py (MATLAB / Octave are not installed): LS estimate, ltf(ind), the isMMSE branch with
+     per-rx SNR, the data-phase case numSTS = 1, and LMMSE_ce called directly with Nps = 2.  helperGetP (a MathWorks
+     example helper that is not in the reference repo) is supplied as Sylvester-Hadamard.  Pins oracle.ls and
+     oracle.lmmse, and through them the CUDA path.
   3. massiveMIMO_dataGenerator.DataGenerator executed unmodified (stub
      ``tensorflow.keras.utils.Sequence``) on a synthetic pickle-shaped dataset
      built with create_massiveMIMO_CSIest_dnn_dataset.py:62's row formula.
@@ -216,7 +221,48 @@ def run_data_generator_reshape():
     return out
 
 
+# ---------------------------------------------------------------- 4. the MATLAB hot path, interpreted
+def run_matlab_hot_path():
+    sys.path.insert(0, HERE)
+    from mini_matlab import MatlabFile
+    pg = os.path.join(REF, "packet_generation", "phased_arr")
+    src_h = open(os.path.join(pg, "helperMIMOChannelEstimate.m"), encoding="latin-1").read()
+    src_l = open(os.path.join(pg, "LMMSE_ce.m"), encoding="latin-1").read()
+
+    def hadamard(n):
+        n = int(np.asarray(n).item())
+        H = np.ones((1, 1))
+        while H.shape[0] < n:
+            H = np.block([[H, H], [H, -H]])
+        return H
+
+    m = MatlabFile(src_h, src_l, externals={"helperGetP": hadamard})
+    tabs = parse_tables()
+    car = tabs["carriers"].astype(np.float64).reshape(-1, 1)
+    rng = np.random.default_rng(67)
+    out = {}
+    # A: sounding phase, 4 x 2, isMMSE = true with SNR(i) per rx and a delay vector as LMMSE_ce's `h`
+    # B: 8 x 3, isMMSE = false        C: data phase numSTS = nltf = 1 (generate_maMIMO_LTF.m:578)
+    for tag, nt, nr, mmse in (("A", 4, 2, 1.0), ("B", 8, 3, 0.0), ("C", 1, 2, 0.0)):
+        rx = rng.standard_normal((car.size, nt, nr)) + 1j * rng.standard_normal((car.size, nt, nr))
+        tau = np.abs(rng.standard_normal((1, 100))) * 2.5
+        snr = rng.uniform(0.0, 25.0, (nr, 1))
+        prm = {"numSTS": float(nt), "CarriersLocations": car}
+        hD, P, ltf_o, hM = m.call("helperMIMOChannelEstimate", [rx, prm, 1.0, tau, snr, mmse], 4)
+        out.update({"rx_" + tag: rx, "tau_" + tag: tau, "snr_" + tag: snr, "hD_" + tag: hD, "P_" + tag: P,
+                    "ltf_o_" + tag: ltf_o, "hDmmse_" + tag: hM})
+    # LMMSE_ce called directly: comb pilots Nps = 2, and the reference-style tiny delays (seconds) at 30 dB
+    for tag, n, nps, h, snr in (("nps2", 48, 2.0, np.exp(-np.arange(8) / 3.0).reshape(1, -1), 12.0),
+                                ("sec", 64, 1.0, np.abs(rng.standard_normal((1, 100))) * 1e-7, 30.0)):
+        x = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1))
+        y = m.call("LMMSE_ce", [x, float(n), float(n), nps, h, snr], 1)[0]
+        out.update({"ce_x_" + tag: x, "ce_h_" + tag: h, "ce_y_" + tag: y, "ce_par_" + tag: np.array([n, nps, snr])})
+    out["carriers"] = tabs["carriers"]
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "ref_matlab_ls_lmmse.npz"), **run_matlab_hot_path())
     install_stub_tf(lambda path: None)
     np.savez_compressed(os.path.join(HERE, "ref_data_generator_reshape.npz"), **run_data_generator_reshape())
     np.savez_compressed(os.path.join(HERE, "ref_tables.npz"), **parse_tables())

@@ -1,0 +1,99 @@
+"""Golden vectors produced by running the reference's own MATLAB source text (helperMIMOChannelEstimate.m,
+LMMSE_ce.m) through tests/golden/mini_matlab.py in the build container (tests/golden/make_golden.py section 4;
+MATLAB / Octave are not installed).  CPU part: the numpy oracle reproduces them (this PINS oracle.ls and
+oracle.lmmse); GPU part: the CUDA path reproduces them through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import mamimo_b200 as mm
+from oracle import ls, lmmse, tables
+from _util import rel_l2
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_matlab_ls_lmmse.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ interpreter sanity
+def test_mini_matlab_semantics():
+    from mini_matlab import MatlabFile
+    src = """
+function [a,b,c,d,e] = probe(x, s)
+v = [1; 2;-3; 4];            % column literal, '-3' is an element
+r = [0:3].';                 % range in brackets, plain transpose
+a = v(2:end) .* r(1:3) - 1./[2 4 8].';
+M = repmat([1 2 3], 2, 1);   b = M(:, [1 3])' * [1; 1i];
+c = zeros(2,3,2);  for k = 1:2, c(:,k,2) = [k; 10*k]; end
+q = x*x';  d = sum(x.*conj(x))/q + 10^(s*0.1) + numel(M) + length(v) + size(M,2);
+[~, n2] = size(M);  if n2 == 3 && ~(n2 < 1), e = x(end)^2; else, e = 0; end
+end
+"""
+    m = MatlabFile(src)
+    a, b, c, d, e = m.call("probe", [np.array([[1 + 2j, 3.0]]), 20.0], 5)
+    assert np.allclose(a.ravel(), [2 * 0 - 0.5, -3 * 1 - 0.25, 4 * 2 - 0.125])
+    assert np.allclose(b, np.array([[1 + 1j], [3 + 3j]]))          # M(:,[1 3])' is 2x2 [[1,1],[3,3]]
+    assert c.shape == (2, 3, 2) and np.allclose(c[:, :, 1], [[1, 2, 0], [10, 20, 0]]) and not c[:, :, 0].any()
+    assert np.allclose(d, 1.0 + 100.0 + 6 + 4 + 3)
+    assert np.allclose(e, 9.0)
+
+
+# ------------------------------------------------------------------------------------------------ oracle pinned
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_oracle_ls_reproduces_interpreted_matlab(g, tag):
+    rx, P, hD = g["rx_" + tag], g["P_" + tag], g["hD_" + tag]
+    assert np.array_equal(g["ltf_o_" + tag].ravel(), tables.ltf_at_carriers())        # ltf(ind), :29
+    assert np.array_equal(g["carriers"], tables.carriers_locations())
+    ours = ls.ls_estimate_loop(rx, P, tables.ltf_at_carriers())
+    assert rel_l2(hD, ours) <= 1e-15
+    batched = ls.ls_estimate(ls.mat_to_batched(rx), P, tables.ltf_at_carriers())[0]
+    assert rel_l2(hD, ls.batched_to_mat(batched)) <= 1e-15
+    if tag != "A":
+        assert not g["hDmmse_" + tag].any()                                           # isMMSE = false: zeros (:32)
+
+
+def test_oracle_lmmse_reproduces_interpreted_matlab(g):
+    hD, tau, snr = g["hD_A"], g["tau_A"].ravel(), g["snr_A"].ravel()
+    assert rel_l2(g["hDmmse_A"], lmmse.helper_mmse_loop(hD, 1, tau, snr)) <= 1e-12
+    bat = lmmse.lmmse_batched(np.transpose(hD, (2, 1, 0))[None], lmmse.tau_rms(tau), snr[None], 1)[0]
+    assert rel_l2(g["hDmmse_A"], np.transpose(bat, (2, 1, 0))) <= 1e-12
+    for tag in ("nps2", "sec"):
+        n, nps, s = g["ce_par_" + tag]
+        y = lmmse.lmmse_ce(g["ce_x_" + tag].ravel(), int(n), int(n), int(nps), g["ce_h_" + tag].ravel(), float(s))
+        assert rel_l2(g["ce_y_" + tag].ravel(), y) <= 1e-12
+        assert mm.tau_rms(g["ce_h_" + tag].ravel()) == pytest.approx(lmmse.tau_rms(g["ce_h_" + tag].ravel()), rel=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["A", "B", "C"])
+def test_cuda_ls_reproduces_interpreted_matlab(g, tag):
+    rx, P = g["rx_" + tag], g["P_" + tag]
+    prm = {"numSTS": P.shape[0], "CarriersLocations": g["carriers"]}
+    hD, Pm, ltf_o, hM = mm.helperMIMOChannelEstimate(rx, prm, 1, None, None, False, P=P)
+    assert rel_l2(g["hD_" + tag], hD) <= 1e-6                      # FP32 arithmetic vs MATLAB double
+    assert np.array_equal(ltf_o, g["ltf_o_" + tag]) and not hM.any()
+
+
+@pytest.mark.gpu
+def test_cuda_lmmse_reproduces_interpreted_matlab(g):
+    rx, P = g["rx_A"], g["P_A"]
+    prm = {"numSTS": P.shape[0], "CarriersLocations": g["carriers"]}
+    hD, _, _, hM = mm.helperMIMOChannelEstimate(rx, prm, 1, g["tau_A"].ravel(), g["snr_A"].ravel(), True, P=P)
+    assert rel_l2(g["hDmmse_A"], hM) <= 1e-6                       # LS in FP32 feeds the FP64 smoother
+    # the smoother alone, fed MATLAB's own hD: FP64 end to end
+    nt, nr = P.shape[0], rx.shape[2]
+    with mm.Engine(nt, nr, rx.shape[0], mlp=False) as eng:
+        out = eng.lmmse(np.ascontiguousarray(np.transpose(g["hD_A"], (2, 1, 0))[None]), lmmse.tau_rms(g["tau_A"].ravel()),
+                        g["snr_A"].ravel()[None])
+    assert rel_l2(g["hDmmse_A"], np.transpose(out[0], (2, 1, 0))) <= 1e-9
+    for tag in ("nps2", "sec"):
+        n, nps, s = g["ce_par_" + tag]
+        with mm.Engine(1, 1, int(n), n_ltf=1, n_ps=int(nps), mlp=False) as eng:
+            y = eng.lmmse(g["ce_x_" + tag].reshape(1, 1, 1, -1), lmmse.tau_rms(g["ce_h_" + tag].ravel()), float(s))
+        assert rel_l2(g["ce_y_" + tag].ravel(), y.ravel()) <= 1e-9
