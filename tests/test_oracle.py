@@ -107,3 +107,34 @@ def test_renew_layout_round_trip():
     assert np.array_equal(postproc.renew_postprocess(sel), v)
     with pytest.raises(ValueError):
         postproc.renew_postprocess(np.zeros((1, 51)))
+
+
+def test_mlp_oracle_matches_independent_torch_layers():
+    """TensorFlow cannot run here, so the Keras layer arithmetic of oracle.mlp (Dense: x @ W + b, relu, then
+    BatchNormalization at inference: gamma * (x - mean) / sqrt(var + 1e-3) + beta, ..._DNN.py:211-227) is cross-checked
+    against an independent library implementing the same documented layers: torch.nn.Linear / ReLU /
+    BatchNorm1d(eps=1e-3).eval() in float64."""
+    import torch
+    import mamimo_b200 as mm
+    nets = mm.synth.make_nets(40, (64, 48), 30)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((17, 40))
+    for name in ("real", "imag"):
+        mods = []
+        for li, L in enumerate(nets[name]):
+            lin = torch.nn.Linear(L["W"].shape[0], L["W"].shape[1]).double()
+            lin.weight.data = torch.from_numpy(np.asarray(L["W"], np.float64).T.copy())     # Keras kernel is [in, out]
+            lin.bias.data = torch.from_numpy(np.asarray(L["b"], np.float64).copy())
+            mods.append(lin)
+            if li < len(nets[name]) - 1:
+                mods.append(torch.nn.ReLU())
+                g, be, mu, var = (torch.from_numpy(np.asarray(t, np.float64).copy()) for t in L["bn"])
+                bn = torch.nn.BatchNorm1d(g.numel(), eps=1e-3).double()
+                bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var = g, be, mu, var
+                mods.append(bn)
+        net = torch.nn.Sequential(*mods).eval()
+        with torch.no_grad():
+            ref = net(torch.from_numpy(x)).numpy()
+        got = mlp.forward(x, nets[name])
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
+        assert np.linalg.norm(mlp.forward(x, mlp.fold_bn(nets[name])) - ref) / np.linalg.norm(ref) < 1e-12
