@@ -19,7 +19,8 @@ Pinning status (see DESIGN.md "Oracle"):
   against the reference's own MATLAB source text, executed unmodified by the MATLAB-subset interpreter
   ``tests/golden/mini_matlab.py`` (MATLAB / Octave are not installed): ``tests/golden/ref_matlab_ls_lmmse.npz``,
   checked in ``tests/test_golden_matlab.py`` (LS 1e-16, LMMSE 1e-12 incl. per-rx SNR, Nps = 2 and the data-phase
-  numSTS = 1 case).  ``helperGetP`` (a MathWorks example helper, not in the reference repo) is input data there.
+  numSTS = 1 case); the same file pins ``postproc.nmse_subk`` / ``rows_to_csi`` on BER_test_maMIMO_LTF.m's own
+  text.  ``helperGetP`` (a MathWorks example helper, not in the reference repo) is input data there.
 * ``oracle.mlp`` (Keras FC graph) restates TensorFlow layer semantics that cannot run here (no TensorFlow / h5py):
   **parity unpinned** by execution of TensorFlow itself; the glue around it (``CSIPredictor.inference`` end to end
   with a numpy Keras stand-in) is pinned, and the layer arithmetic is anchored on BN-fold == unfused identities.

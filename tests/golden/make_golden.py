@@ -258,6 +258,24 @@ def run_matlab_hot_path():
         y = m.call("LMMSE_ce", [x, float(n), float(n), nps, h, snr], 1)[0]
         out.update({"ce_x_" + tag: x, "ce_h_" + tag: h, "ce_y_" + tag: y, "ce_par_" + tag: np.array([n, nps, snr])})
     out["carriers"] = tabs["carriers"]
+    # NMSE_subk (sub-function at the end of BER_test_maMIMO_LTF.m, :675-686) and the loop that rebuilds
+    # CSI(:,iTX,iRX) from the prediction rows (:213-218; the literal lines wrapped in a function header)
+    ber = open(os.path.join(pg, "BER_test_maMIMO_LTF.m"), encoding="latin-1").read()
+    sub = ber[ber.index("function [out] = NMSE_subk"):]
+    lines = ber.splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.strip().startswith("for iRX = 1:nRXAnts"))
+    loop = "\n".join(lines[i0:i0 + 6])
+    assert "CSI_dnn_imag(:,iTX,iRX)" in loop and loop.rstrip().endswith("end")
+    wrap = ("function [CSI_dnn_real, CSI_dnn_imag] = rebuild(predicted_CSI_real, predicted_CSI_imag, nRXAnts, nTXAnts)\n"
+            + loop + "\nend\n")
+    m2 = MatlabFile(sub, wrap)
+    Href = rng.standard_normal((52, 4, 3)) + 1j * rng.standard_normal((52, 4, 3))
+    Hest = Href + 0.1 * (rng.standard_normal((52, 4, 3)) + 1j * rng.standard_normal((52, 4, 3)))
+    out.update(nmse_ref=Href, nmse_est=Hest, nmse_val=m2.call("NMSE_subk", [Href, Hest], 1)[0],
+               nmse_zero=m2.call("NMSE_subk", [Href, Href], 1)[0], nmse_one=m2.call("NMSE_subk", [Href, 0 * Href], 1)[0])
+    pr, pi = rng.standard_normal((12, 52)), rng.standard_normal((12, 52))
+    cr, ci = m2.call("rebuild", [pr, pi, 3.0, 4.0], 2)
+    out.update(rebuild_pred_real=pr, rebuild_pred_imag=pi, rebuild_csi_real=cr, rebuild_csi_imag=ci)
     return out
 
 

@@ -13,8 +13,8 @@ generated from the reference itself rather than from a hand translation:
   sub-functions;
 * expressions: numbers, ``i``/``j`` imaginary unit when not shadowed, matrix literals with ``,`` / blank / ``;``,
   ranges, ``end`` inside indices, struct fields, the operators ``+ - * / ^ .* ./ .^ ' .' : < > <= >= == ~= && || ~``;
-* builtins: size zeros ones eye complex numel length squeeze reshape repmat inv sum sqrt conj transpose abs real
-  imag floor mod isempty and a few more; anything else (e.g. ``helperGetP``, a MathWorks example helper that is not
+* builtins: size zeros ones eye complex numel length squeeze reshape repmat inv sum mean norm sqrt conj transpose
+  abs real imag floor mod isempty and a few more; char literals ('all') as option arguments; anything else (e.g. ``helperGetP``, a MathWorks example helper that is not
   in the reference repo) must be supplied by the caller as a Python callable.
 
 It is deliberately general (a tokenizer + recursive-descent parser + tree-walking evaluator), not a line-by-line
@@ -100,6 +100,21 @@ def tokenize(src):
     text = re.sub(r"\.\.\.[^\n]*\n", " ", text)
     toks, pos, space = [], 0, False
     while pos < len(text):
+        if text[pos] == "'":
+            prev = toks[-1] if toks else None
+            operand = prev is not None and not space and (prev.kind in ("id", "num") or prev.text in (")", "]", "}", "'", ".'"))
+            if not operand:                       # a quote that does not follow an operand opens a char literal
+                end = pos + 1
+                while True:
+                    end = text.index("'", end)
+                    if text[end:end + 2] == "''":
+                        end += 2
+                        continue
+                    break
+                toks.append(Tok("str", text[pos + 1:end].replace("''", "'"), space))
+                space = False
+                pos = end + 1
+                continue
         m = _TOKEN.match(text, pos)
         if not m:
             raise MatlabError("cannot tokenize at %r" % text[pos:pos + 30])
@@ -381,6 +396,8 @@ class Parser:
 
     def parse_primary(self):
         tok = self.next()
+        if tok.kind == "str":
+            return ("str", tok.text.strip('"'))
         if tok.kind == "num":
             if tok.text[-1] in "ij":
                 return ("num", 1j * float(tok.text[:-1]))
@@ -520,6 +537,21 @@ class MatlabFile:
             return [np.swapaxes(A[0], 0, 1)]
         if name == "ctranspose":
             return [np.conj(np.swapaxes(A[0], 0, 1))]
+        if name == "norm":
+            x = A[0]
+            if min(x.shape) == 1 or x.ndim > 2:
+                return [mat(np.sqrt(np.sum(np.abs(x) ** 2)))]
+            return [mat(np.linalg.norm(x, 2))]
+        if name == "mean":
+            x = A[0]
+            if len(A) == 2 and isinstance(A[1], str):
+                if A[1] != "all":
+                    raise MatlabError("mean: unsupported option %r" % A[1])
+                return [mat(np.mean(x))]
+            if len(A) == 2:
+                return [np.mean(x, axis=int(A[1].item()) - 1, keepdims=True)]
+            ax = next((i for i, s in enumerate(x.shape) if s != 1), 0)
+            return [np.mean(x, axis=ax, keepdims=True)]
         if name == "mod":
             return [np.mod(A[0], A[1])]
         if name == "isempty":
@@ -616,6 +648,8 @@ class MatlabFile:
         k = node[0]
         if k == "num":
             return mat(node[1])
+        if k == "str":
+            return node[1]
         if k == "paren":
             return self._eval(node[1], env)
         if k == "endidx":
@@ -753,6 +787,14 @@ class MatlabFile:
                 env[name] = flat.reshape(cur.shape, order="F")
                 return
             shp = list(cur.shape) + [1] * max(0, n - cur.ndim)
+            if cur.size == 0:
+                # A(:,j,i) = v on an undefined / empty A: the colon dimension takes its extent from v
+                shp = [0] * n
+                fixed = int(np.prod([np.asarray(ix).size for ix in idx if not _is_colon(ix)])) or 1
+                colons = [d for d, ix in enumerate(idx) if _is_colon(ix)]
+                for d in colons:
+                    shp[d] = val.size // fixed if len(colons) == 1 else val.shape[d] if d < val.ndim else 1
+                cur = np.zeros(shp, dtype=val.dtype)
             lists = []
             for d, ix in enumerate(idx):
                 lists.append(_index_list(ix, shp[d] if d < len(shp) else 1))

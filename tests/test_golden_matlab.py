@@ -69,6 +69,22 @@ def test_oracle_lmmse_reproduces_interpreted_matlab(g):
         assert mm.tau_rms(g["ce_h_" + tag].ravel()) == pytest.approx(lmmse.tau_rms(g["ce_h_" + tag].ravel()), rel=1e-13)
 
 
+def test_oracle_nmse_and_pair_rebuild_reproduce_interpreted_matlab(g):
+    """NMSE_subk (BER_test_maMIMO_LTF.m:675-686) and the loop that rebuilds CSI(:,iTX,iRX) from prediction rows
+    (:213-218), both executed from the reference's text."""
+    from oracle import postproc
+    assert postproc.nmse_subk(g["nmse_ref"], g["nmse_est"]) == pytest.approx(g["nmse_val"].item(), rel=1e-13)
+    assert g["nmse_zero"].item() == 0.0 and g["nmse_one"].item() == pytest.approx(1.0, rel=1e-15)
+    pr, pi = g["rebuild_pred_real"], g["rebuild_pred_imag"]
+    n_tx, n_rx = g["rebuild_csi_real"].shape[1:]
+    csi = postproc.rows_to_csi(pr + 1j * pi, n_tx, n_rx)
+    assert np.array_equal(csi.real, g["rebuild_csi_real"]) and np.array_equal(csi.imag, g["rebuild_csi_imag"])
+    for i_rx in range(n_rx):                                   # the C ABI's row formula is the inverse of that loop
+        for i_tx in range(n_tx):
+            row = mm.pair_row(0, i_rx, i_tx, n_rx, n_tx)
+            assert np.array_equal(g["rebuild_csi_real"][:, i_tx, i_rx], pr[row])
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["A", "B", "C"])
