@@ -151,6 +151,34 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are
+    allocated (first touch places them on that node): the end-to-end path is PCIe/host-memory bound and with several
+    ranks the default placement sends DMA traffic across sockets."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus or cpus == allowed:
+            return "node %d (no change)" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d, %d cpus" % (node, len(cpus))
+    except Exception as ex:                                  # containers often hide the topology: not an error
+        return "unavailable (%s)" % type(ex).__name__
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -164,6 +192,7 @@ def run_ours(args):
         raise SystemExit("bench.py (our arm) needs a B200: no CUDA device visible, and there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else "off"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -361,6 +390,7 @@ def run_ours(args):
                        "l2": "inputs (0.5 GiB Y) and outputs (0.5 GiB) per step exceed the 126 MB L2",
                        "launch": "value: one CUDA-graph launch per step (7 kernels); rooflines: the same K steps re-run after "
                                  "1 s idle as plain launches with per-kernel CUDA events (ms_per_step_profiled)",
+                       "numa_bind": numa_note,
                        "parallelism": "packets sharded over %d GPU(s)%s" % (
                            world, (", all-gather of H planes in step (%s)" % gather_note) if world > 1 else "")},
             "clocks": clocks,
@@ -396,6 +426,7 @@ def main():
     ap.add_argument("--max-pkts", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how H-hat is all-gathered")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
     args = ap.parse_args()
