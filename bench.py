@@ -203,13 +203,16 @@ def run_ours(args):
     gen_pkts = min(npkt, args.gen_pkts)
     Yg, _ = mm.synth.make_packets(1, gen_pkts, NT, NR, NSC, SNR_DB, x_tones=x, first_pkt=rank * npkt)
     reps = (npkt + gen_pkts - 1) // gen_pkts
-    Yh = torch.from_numpy(np.concatenate([Yg] * reps)[:npkt].copy()).pin_memory()
+    Yh = torch.from_numpy(np.concatenate([Yg] * reps)[:npkt].copy())
+    if not args.no_e2e:
+        Yh = Yh.pin_memory()
     Yd = Yh.to(dev)
     rows = npkt * NT * NR
     Hr = torch.empty((rows, NSC), dtype=torch.float32, device=dev)
     Hi = torch.empty_like(Hr)
-    Hr_h = torch.empty((rows, NSC), dtype=torch.float32).pin_memory()
-    Hi_h = torch.empty((rows, NSC), dtype=torch.float32).pin_memory()
+    host_rows = 64 if args.no_e2e else rows
+    Hr_h = torch.empty((host_rows, NSC), dtype=torch.float32).pin_memory()
+    Hi_h = torch.empty((host_rows, NSC), dtype=torch.float32).pin_memory()
     gathered = None
     if world > 1:
         gathered = [torch.empty((world * rows, NSC), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -333,19 +336,20 @@ def run_ours(args):
     def step_host():
         eng.estimate_raw(Yh.data_ptr(), 0, npkt, 0, Hr_h.data_ptr(), Hi_h.data_ptr(), 0)
 
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for _ in range(2 if e2e_steps else 0):
         step_host()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_host()                      # synchronous: returns when H-hat is on the host
     torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = (time.perf_counter() - t0) / max(1, e2e_steps) if e2e_steps else float("inf")
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * npkt / float(t.item())
-    checksum = float(Hr_h[:: max(1, rows // 64)].double().sum().item())    # device->host result actually read
+    checksum = float(Hr_h[:: max(1, host_rows // 64)].double().sum().item()) if e2e_steps else None    # device->host result actually read
 
     # ---- roofline of the dominant kernel (FC layers on the tensor pipe), from the live profile
     peaks, peak_src = measured_peaks()
@@ -394,7 +398,7 @@ def run_ours(args):
                        "parallelism": "packets sharded over %d GPU(s)%s" % (
                            world, (", all-gather of H planes in step (%s)" % gather_note) if world > 1 else "")},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
+            "e2e": {"value": e2e_val if e2e_steps else None, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
                     "d2h_bytes_per_step": int(2 * rows * NSC * 4), "checksum": checksum},
             "gpu_launches": int(launches), "graph_launches": int(eng.stats()["graph_launches"]),
             "roofline": roofline, "roofline_ls": roofline_ls,
@@ -429,7 +433,22 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how H-hat is all-gathered")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (the bench line); c5 = configs[4]: Nt64 Nr8 2048 sc, 3000 packets per GPU "
+                         "processed as 24 steps of 125 with the fused all-gather (gathered chunk consumed/overwritten per step)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer region (c5: 1 GB of pinned buffers per rank)")
     args = ap.parse_args()
+    if args.config == "c5":
+        global NT, NR, NSC, WORKLOAD, MLP_FLOP_PER_PKT, LS_BYTES_PER_PKT
+        NT, NR, NSC = 64, 8, 2048
+        WORKLOAD = ("configs[4]: Nt=64 Nr=8, 2048 sc, 3000 packets per GPU as chunks of %d per step, FC 2048-1024-1024-2048 x2 nets, "
+                    "all-gather of H-hat per chunk" % (125 if args.npkt == 500 else args.npkt))
+        MLP_FLOP_PER_PKT = NT * NR * 2 * 2 * (NSC * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * NSC)
+        LS_BYTES_PER_PKT = NR * NT * NSC * 8 * 2
+        if args.npkt == 500:
+            args.npkt = 125
+        args.gen_pkts = min(args.gen_pkts, 5)
+        args.cpu_sample = min(args.cpu_sample, 16)
     # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library
     import importlib.util
     spec = importlib.util.spec_from_file_location(
