@@ -3,6 +3,8 @@
 Tolerance: the CUDA path solves in FP64 (Cholesky) where the oracle evaluates Rhp*inv(Rpp)*H literally with
 LAPACK's inverse; they agree to cond(Rpp)*eps.  rel-L2 <= 1e-9 for complex128 I/O at SNR <= 30 dB, <= 2e-7 for
 complex64 I/O (output rounding), 1e-5 (the north_star bound) at 60 dB where cond(Rpp) ~ 1e8."""
+import os
+
 import numpy as np
 import pytest
 
@@ -86,3 +88,34 @@ def test_lmmse_pilot_spacing_and_chunking_and_device_buffers(monkeypatch):
         eng.synchronize()
     assert rel_l2(lmmse.lmmse_batched(H, 2.0, snr, 1), a) <= 1e-9
     assert np.array_equal(a, b.cpu().numpy())                      # host and device paths are the same kernels
+
+
+@pytest.mark.parametrize("nt,nr,nsc,npkt", [(1, 1, 31, 2), (1, 3, 33, 1), (2, 1, 32, 3), (40, 1, 65, 1), (64, 8, 64, 2)])
+@pytest.mark.parametrize("route", ["1", "0"])
+def test_lmmse_edge_shapes_both_routes(nt, nr, nsc, npkt, route, monkeypatch):
+    """block-size edges (Nsc below / at / just above a 32-block), a single right-hand side, more right-hand sides than
+    one solve CTA holds (40, 64), for the Toeplitz route and the dense-Cholesky cross-check route"""
+    monkeypatch.setenv("MAMIMO_LMMSE_SCHUR", route)
+    rng = np.random.default_rng(nsc * 7 + nt)
+    H = _h(rng, npkt, nr, nt, nsc, np.complex128)
+    t_rms = rng.uniform(0.2, 8.0, npkt)
+    snr = rng.uniform(-10.0, 35.0, (npkt, nr))
+    with mm.Engine(nt, nr, nsc, mlp=False) as eng:
+        out = eng.lmmse(H, t_rms, snr)
+    assert rel_l2(lmmse.lmmse_batched(H, t_rms, snr, 1), out) <= 1e-9
+
+
+def test_lmmse_routes_agree_and_empty_batch():
+    rng = np.random.default_rng(12)
+    nt, nr, nsc = 8, 2, 100
+    H = _h(rng, 3, nr, nt, nsc, np.complex128)
+    outs = []
+    for route in ("1", "0"):
+        os.environ["MAMIMO_LMMSE_SCHUR"] = route
+        try:
+            with mm.Engine(nt, nr, nsc, mlp=False) as eng:
+                outs.append(eng.lmmse(H, 2.0, 15.0))
+                assert eng.lmmse(H[:0], 2.0, 15.0).shape == (0, nr, nt, nsc)
+        finally:
+            os.environ.pop("MAMIMO_LMMSE_SCHUR", None)
+    assert rel_l2(outs[1], outs[0]) <= 1e-11

@@ -426,6 +426,29 @@ def test_ofdm_demod_parity(fft_len, cp, so, nt, nr, ctype):
     assert rel_l2(ref, Y) <= 2e-6                             # FP32 FFT vs FP64 oracle
 
 
+@pytest.mark.parametrize("fft_len,cp,so", [(1024, 73, 73), (1024, 72, 41), (256, 64, 0), (2048, 0, 0), (512, 128, 128)])
+def test_ofdm_demod_kernel_variants_agree(fft_len, cp, so, monkeypatch):
+    """odd cyclic prefix / offset take the plain register-FFT kernel, even ones the bulk-copy-fed persistent kernel,
+    MAMIMO_OFDM_GENERIC the radix-4 Stockham kernel: all against the oracle, and the two register kernels bitwise"""
+    from oracle import ofdm
+    rng = np.random.default_rng(fft_len + cp)
+    nt, nr, npkt = 3, 2, 5                                    # 30 symbols: partial last tile for every FFT size
+    car = np.arange(5, fft_len - 7, dtype=np.int32)
+    x = (rng.standard_normal((npkt, nr, nt * (fft_len + cp))) + 1j * rng.standard_normal((npkt, nr, nt * (fft_len + cp)))).astype(np.complex64)
+    ref = ofdm.ofdm_demod(x, fft_len, cp, so, car)
+    outs = {}
+    for name, env in (("tma", {}), ("plain", {"MAMIMO_OFDM_TMA": "0"}), ("generic", {"MAMIMO_OFDM_GENERIC": "1"})):
+        for k in ("MAMIMO_OFDM_TMA", "MAMIMO_OFDM_GENERIC"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with mm.Engine(nt, nr, car.size, mlp=False) as eng:
+            eng.set_ofdm(fft_len, cp, so, car)
+            outs[name] = eng.ofdm_demod(x)
+        assert rel_l2(ref, outs[name]) <= 2e-6, name
+    assert np.array_equal(outs["tma"], outs["plain"])         # same passes, same arithmetic order
+
+
 def test_estimate_from_time_domain_reference_numerology():
     """Time-domain preamble -> ofdmdemod -> LS -> FC with the reference's 256/64/234 numerology, against
     oracle demod + oracle LS + oracle FC; also equals the two-call path (demod, then estimate) bitwise."""
