@@ -1523,25 +1523,37 @@ mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_ty
   const int nb = (n + kLmNB - 1) / kLmNB, n_pad = nb * kLmNB, nt_pad = round_up(nt, 8), R = n_pad + nt_pad;
   const int64_t n_slab = n_pkt * nrx;
   const size_t per_slab = (static_cast<size_t>(R) * n_pad + static_cast<size_t>(nb) * kLmNB * kLmNB) * sizeof(double2);
-  if (!e->lm_M) {
+  {
     size_t budget = static_cast<size_t>(8) << 30;                       // workspace budget (MAMIMO_LMMSE_WS_MB)
     if (const char* env = getenv("MAMIMO_LMMSE_WS_MB")) if (atoll(env) > 0) budget = static_cast<size_t>(atoll(env)) << 20;
-    size_t free_b = 0, total_b = 0;
-    CK(e, cudaMemGetInfo(&free_b, &total_b));
-    budget = std::min(budget, free_b / 2);
     const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(static_cast<int64_t>(budget / per_slab), 32768));
-    e->lm_slabs = static_cast<int>(std::min<int64_t>(cap, std::max<int64_t>(n_slab, 4LL * nrx)));
-    CK(e, cudaMalloc(&e->lm_M, static_cast<size_t>(e->lm_slabs) * R * n_pad * sizeof(double2)));
-    CK(e, cudaMalloc(&e->lm_Dinv, static_cast<size_t>(e->lm_slabs) * nb * kLmNB * kLmNB * sizeof(double2)));
-    CK(e, cudaMalloc(&e->lm_par, static_cast<size_t>(e->lm_slabs) * sizeof(double2)));
-    CK(e, cudaFuncSetAttribute(lmmse_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmPanelSmem));
-    CK(e, cudaFuncSetAttribute(lmmse_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
-    CK(e, cudaFuncSetAttribute(lmmse_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
-    if (2 * n_pad * sizeof(double2) > 48 * 1024)
-      CK(e, cudaFuncSetAttribute(lmmse_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(2 * n_pad * sizeof(double2))));
-    if (const char* env = getenv("MAMIMO_LMMSE_SCHUR")) e->lm_schur = atoi(env) != 0;
-    for (int i = 0; i < 4; ++i) CK(e, cudaEventCreateWithFlags(&e->lm_ev[i], cudaEventDisableTiming));
-    if (const char* env = getenv("MAMIMO_LMMSE_STREAMS")) if (atoi(env) > 0) e->lm_groups = atoi(env);
+    const int want = static_cast<int>(std::min<int64_t>(cap, std::max<int64_t>(n_slab, 4LL * nrx)));
+    if (want > e->lm_slabs) {                                            // first call, or a larger batch than before
+      CK(e, cudaDeviceSynchronize());
+      if (e->lm_M) cudaFree(e->lm_M);
+      if (e->lm_Dinv) cudaFree(e->lm_Dinv);
+      if (e->lm_par) cudaFree(e->lm_par);
+      e->lm_M = e->lm_Dinv = e->lm_par = nullptr;
+      const bool first = e->lm_slabs == 0;
+      e->lm_slabs = 0;
+      size_t free_b = 0, total_b = 0;
+      CK(e, cudaMemGetInfo(&free_b, &total_b));
+      const int fit = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, (free_b / 2) / per_slab)));
+      CK(e, cudaMalloc(&e->lm_M, static_cast<size_t>(fit) * R * n_pad * sizeof(double2)));
+      CK(e, cudaMalloc(&e->lm_Dinv, static_cast<size_t>(fit) * nb * kLmNB * kLmNB * sizeof(double2)));
+      CK(e, cudaMalloc(&e->lm_par, static_cast<size_t>(fit) * sizeof(double2)));
+      e->lm_slabs = fit;
+      if (first) {
+        CK(e, cudaFuncSetAttribute(lmmse_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmPanelSmem));
+        CK(e, cudaFuncSetAttribute(lmmse_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
+        CK(e, cudaFuncSetAttribute(lmmse_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBsSmem));
+        if (2 * n_pad * sizeof(double2) > 48 * 1024)
+          CK(e, cudaFuncSetAttribute(lmmse_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(2 * n_pad * sizeof(double2))));
+        if (const char* env = getenv("MAMIMO_LMMSE_SCHUR")) e->lm_schur = atoi(env) != 0;
+        for (int i = 0; i < 4; ++i) CK(e, cudaEventCreateWithFlags(&e->lm_ev[i], cudaEventDisableTiming));
+        if (const char* env = getenv("MAMIMO_LMMSE_STREAMS")) if (atoi(env) > 0) e->lm_groups = atoi(env);
+      }
+    }
   }
   const size_t in_el = h_type == MAMIMO_C128 ? 16 : 8, out_el = out_type == MAMIMO_C128 ? 16 : 8;
   const size_t slab_el = static_cast<size_t>(nt) * n;

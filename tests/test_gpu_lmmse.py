@@ -119,3 +119,17 @@ def test_lmmse_routes_agree_and_empty_batch():
         finally:
             os.environ.pop("MAMIMO_LMMSE_SCHUR", None)
     assert rel_l2(outs[1], outs[0]) <= 1e-11
+
+
+def test_lmmse_workspace_grows_with_the_batch():
+    """first call small, later call larger on the same engine (the workspace is re-sized, not chunked by the first size)"""
+    rng = np.random.default_rng(13)
+    nt, nr, nsc = 4, 2, 48
+    with mm.Engine(nt, nr, nsc, mlp=False) as eng:
+        for npkt in (1, 40, 3):
+            H = _h(rng, npkt, nr, nt, nsc, np.complex128)
+            snr = rng.uniform(0.0, 20.0, (npkt, nr))
+            l0 = eng.stats()["kernel_launches"]
+            out = eng.lmmse(H, 1.5, snr)
+            assert rel_l2(lmmse.lmmse_batched(H, 1.5, snr, 1), out) <= 1e-9
+            assert eng.stats()["kernel_launches"] - l0 <= 3 * 4          # one chunk: (schur, linv, solve) x <= 4 stream groups

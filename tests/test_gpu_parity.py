@@ -40,6 +40,19 @@ def test_ls_hadamard_parity(nt, nr, nsc, npkt, ctype):
     assert rel_l2(hD, np.transpose(H[0], (2, 1, 0))) <= TOL_LS
 
 
+@pytest.mark.parametrize("nt,nr,nsc,npkt", [(32, 4, 234, 3), (32, 2, 52, 2), (64, 2, 234, 2), (32, 1, 2, 1), (32, 3, 190, 5), (64, 1, 66, 1)])
+def test_ls_tma_kernel_ragged_tone_counts(nt, nr, nsc, npkt):
+    """32/64 antennas take the persistent TMA-fed kernel; the reference numerology (234 tones) and other tone counts
+    that are not multiples of the 64-tone tile (or of 4, or smaller than one tile) rely on the TMA unit's zero fill
+    and on the generic emit path."""
+    x = tables.ltf_at_carriers().astype(np.float64) if nsc == 234 else mm.synth.make_pilots(nsc)
+    Y, _ = mm.synth.make_packets(31, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    with mm.Engine(nt, nr, nsc, mlp=False) as eng:
+        eng.set_pilots(x, None)
+        H = eng.ls_estimate(Y)
+    assert rel_l2(oracle_ls(Y, tables.sylvester_hadamard(nt), x), H) <= TOL_LS
+
+
 @pytest.mark.parametrize("nt", [4, 6, 32])
 def test_ls_dense_p_parity(nt):
     rng = np.random.default_rng(5)
