@@ -146,6 +146,7 @@ struct mamimo_engine {
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
   bool small_batch_overlap = true;   // MAMIMO_SMALL_OVERLAP=0: never run the two nets on two streams
+  bool always_overlap = true;        // two streams at every batch size (MAMIMO_SMALL_OVERLAP=1: small batches only)
   uint64_t graph_stamp = 0, graph_replays = 0;
   mamimo_stats stats;
   // optional per-kernel-class device timing (mamimo_profile_begin/end)
@@ -929,7 +930,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
-  if (const char* env = getenv("MAMIMO_SMALL_OVERLAP")) e->small_batch_overlap = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_SMALL_OVERLAP")) { e->small_batch_overlap = atoi(env) != 0; e->always_overlap = atoi(env) != 1; }
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
@@ -1227,14 +1228,17 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
       CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
       return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 2u, true, L - 1, L)));
     }
-    if (!gather && nets == 3u && e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT && e->small_batch_overlap) {
-      // latency regime: the tiles of BOTH nets' layers fit the CTA pairs of the machine at once, so the two
-      // (independent) nets run side by side on two streams instead of back to back (measured: one 32x4x1024 packet
-      // 152 -> 79 us device-resident, 239 -> 164 us from host buffers)
+    if (!gather && nets == 3u && e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT && e->small_batch_overlap &&
+        !e->profiling) {
+      // The two (independent) nets run on two streams / graph branches instead of back to back.  Small batches are
+      // latency-bound (both nets' tiles fit the machine at once): one 32x4x1024 packet 152 -> 79 us device-resident,
+      // 239 -> 164 us from host buffers.  Large batches: the other net's CTAs fill the half-empty last round of
+      // every persistent layer kernel (13.5 rounds of tiles per layer at 500 packets): 251.3 -> 256.6 k packets/s.
+      // Not while profiling: per-kernel event brackets on two interleaved streams would overlap in time.
       int max_n = e->cfg.d_out;
       for (int i = 0; i < e->cfg.n_hidden; ++i) max_n = std::max(max_n, e->cfg.hidden[i]);
       const int tiles = ((rows + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((max_n + kTcBN - 1) / kTcBN);
-      if (tiles * 2 <= e->fc_sms / 2) {
+      if (tiles * 2 <= e->fc_sms / 2 || e->always_overlap) {
         CK(e, cudaEventRecord(e->ev_side[0], st));
         CK(e, cudaStreamWaitEvent(e->s_side, e->ev_side[0], 0));
         s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, e->s_side, 2u, false)));
