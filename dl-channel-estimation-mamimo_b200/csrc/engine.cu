@@ -450,6 +450,31 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
   return MAMIMO_OK;
 }
 
+// Both nets of a batch: on two streams / graph branches when allowed (see the comment inside), else back to back.
+template <int S>
+mamimo_status run_mlp_both(mamimo_engine* e, int rows, float* hr, float* hi, cudaStream_t st, int l_begin = 0) {
+  if (e->fc_pair && S != kFp32Simt && e->small_batch_overlap && !e->profiling) {
+    // The two (independent) nets run on two streams / graph branches instead of back to back.  Small batches are
+    // latency-bound (both nets' tiles fit the machine at once): one 32x4x1024 packet 152 -> 79 us device-resident,
+    // 239 -> 164 us from host buffers.  Large batches: the other net's CTAs fill the half-empty last round of
+    // every persistent layer kernel (13.5 rounds of tiles per layer at 500 packets): 251.3 -> 256.6 k packets/s.
+    // Not while profiling: per-kernel event brackets on two interleaved streams would overlap in time.
+    int max_n = e->cfg.d_out;
+    for (int i = 0; i < e->cfg.n_hidden; ++i) max_n = std::max(max_n, e->cfg.hidden[i]);
+    const int tiles = ((rows + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((max_n + kTcBN - 1) / kTcBN);
+    if (tiles * 2 <= e->fc_sms / 2 || e->always_overlap) {
+      CK(e, cudaEventRecord(e->ev_side[0], st));
+      CK(e, cudaStreamWaitEvent(e->s_side, e->ev_side[0], 0));
+      mamimo_status s = run_mlp<S>(e, rows, hr, hi, e->s_side, 2u, false, l_begin, e->n_layers);
+      if (s == MAMIMO_OK) s = run_mlp<S>(e, rows, hr, hi, st, 1u, false, l_begin, e->n_layers);
+      CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
+      CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
+      return s;
+    }
+  }
+  return run_mlp<S>(e, rows, hr, hi, st, 3u, false, l_begin, e->n_layers);
+}
+
 template <int S>
 mamimo_status run_ls(mamimo_engine* e, const void* dY, int y_double, int n_pkt, void* dHls, int h_double,
                      bool want_planes, cudaStream_t st) {
@@ -563,7 +588,7 @@ mamimo_status run_mode_a_dedup(mamimo_engine* e, const float* dSr, const float* 
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
   }
-  return run_mlp<S>(e, static_cast<int>(n_prx) * e->cfg.n_tx, hr, hi, st, 3u, false, 1, e->n_layers);
+  return run_mlp_both<S>(e, static_cast<int>(n_prx) * e->cfg.n_tx, hr, hi, st, 1);
 }
 
 // One map per rank: this rank's row slot inside that rank's gathered plane, clipped to the rows of this call.
@@ -1228,26 +1253,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
       CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
       return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 2u, true, L - 1, L)));
     }
-    if (!gather && nets == 3u && e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT && e->small_batch_overlap &&
-        !e->profiling) {
-      // The two (independent) nets run on two streams / graph branches instead of back to back.  Small batches are
-      // latency-bound (both nets' tiles fit the machine at once): one 32x4x1024 packet 152 -> 79 us device-resident,
-      // 239 -> 164 us from host buffers.  Large batches: the other net's CTAs fill the half-empty last round of
-      // every persistent layer kernel (13.5 rounds of tiles per layer at 500 packets): 251.3 -> 256.6 k packets/s.
-      // Not while profiling: per-kernel event brackets on two interleaved streams would overlap in time.
-      int max_n = e->cfg.d_out;
-      for (int i = 0; i < e->cfg.n_hidden; ++i) max_n = std::max(max_n, e->cfg.hidden[i]);
-      const int tiles = ((rows + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((max_n + kTcBN - 1) / kTcBN);
-      if (tiles * 2 <= e->fc_sms / 2 || e->always_overlap) {
-        CK(e, cudaEventRecord(e->ev_side[0], st));
-        CK(e, cudaStreamWaitEvent(e->s_side, e->ev_side[0], 0));
-        s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, e->s_side, 2u, false)));
-        if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, 1u, false)));
-        CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
-        CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
-        return s;
-      }
-    }
+    if (!gather && nets == 3u) return DISPATCH_S(e, (run_mlp_both<S>(e, rows, hr, hi, st)));
     return DISPATCH_S(e, (run_mlp<S>(e, rows, hr, hi, st, nets, gather)));
   };
   // Device-resident full path on a capturable stream: the 7 launches of a batch are captured once per
@@ -1314,7 +1320,7 @@ mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const
   auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
     mamimo_status s = DISPATCH_S(e, (run_stage_planes<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
     if (s != MAMIMO_OK) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n), hr, hi, st)));
+    return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n), hr, hi, st)));
   };
   return run_chunked(e, n_rows, e->max_pkts, X_real, xb, X_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
@@ -1334,7 +1340,7 @@ mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const
       return DISPATCH_S(e, (run_mode_a_dedup<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, hr, hi, st)));
     mamimo_status s = DISPATCH_S(e, (run_stage_time<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
     if (s != MAMIMO_OK) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+    return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, sig_real, xb, sig_imag, xb, nullptr, 0, Y_real, Y_imag, hb, mem,
                      static_cast<cudaStream_t>(stream), stage);
@@ -1515,7 +1521,7 @@ mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype
     if (s != MAMIMO_OK) return s;
     s = DISPATCH_S(e, (run_ls<S>(e, e->d_ydemod, 0, static_cast<int>(n), hls, 0, mlp, st)));
     if (s != MAMIMO_OK || !mlp) return s;
-    return DISPATCH_S(e, (run_mlp<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
+    return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, x, xb, nullptr, 0, H_ls, hlsb, mlp ? H_real : nullptr,
                      mlp ? H_imag : nullptr, hb, mem, static_cast<cudaStream_t>(stream), stage);
