@@ -43,6 +43,46 @@ end
     assert np.allclose(e, 9.0)
 
 
+def test_mini_matlab_array_semantics_against_numpy():
+    """column-major reshape / linear indexing, N-d slicing with end and colon, implicit expansion, matrix vs
+    element-wise operators, right division, conjugate vs plain transpose, struct fields, nested functions"""
+    from mini_matlab import MatlabFile
+    src = """
+function [a,b,c,d,e,f,g,h] = probe(X, prm)
+A = reshape(1:24, [2 3 4]);
+a = A(2, end, 3) + A(end) + numel(A(:, 2:end, [1 4]));
+B = squeeze(A(2, :, :));            b = B(:, 2).' * B(:, 3);
+c = X .* [1; 2] + [10 20 30];       % implicit expansion 2x3 .* 2x1 + 1x3
+d = X * X' / (X * X.' + eye(2));    % mrdivide
+e = helper(prm.gain, X(:));         f = prm.idx(end:-1:1);
+M = zeros(3);  M(2, :) = 1:3;  M(:, 3) = M(:, 3) + [7; 8; 9];  M(end, end) = -M(2, 3);
+g = M;  h = sum(sum(M > 0)) + any_neg(M);
+end
+function y = helper(gain, v)
+y = gain * (v' * v) ^ 0.5 + length(v);
+end
+function t = any_neg(M)
+t = 0;
+for k = 1:numel(M), if M(k) < 0, t = t + 1; end, end
+end
+"""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((2, 3)) + 1j * rng.standard_normal((2, 3))
+    prm = {"gain": 2.5, "idx": np.array([[4.0, 5.0, 6.0]])}
+    a, b, c, d, e, f, g, h = MatlabFile(src).call("probe", [X, prm], 8)
+    A = np.arange(1, 25).reshape((2, 3, 4), order="F")
+    assert a.item() == A[1, 2, 2] + A.ravel(order="F")[-1] + A[:, 1:, [0, 3]].size
+    B = A[1, :, :]
+    assert b.item() == B[:, 1] @ B[:, 2]
+    assert np.allclose(c, X * np.array([[1], [2]]) + np.array([[10, 20, 30]]))
+    assert np.allclose(d, (X @ X.conj().T) @ np.linalg.inv(X @ X.T + np.eye(2)))
+    v = X.ravel(order="F")
+    assert np.allclose(e, 2.5 * np.sqrt(np.vdot(v, v)) + 6)
+    assert np.array_equal(f, [[6.0, 5.0, 4.0]])
+    M = np.zeros((3, 3)); M[1, :] = [1, 2, 3]; M[:, 2] += [7, 8, 9]; M[2, 2] = -M[1, 2]
+    assert np.array_equal(g, M) and h.item() == (M > 0).sum() + 1
+
+
 # ------------------------------------------------------------------------------------------------ oracle pinned
 @pytest.mark.parametrize("tag", ["A", "B", "C"])
 def test_oracle_ls_reproduces_interpreted_matlab(g, tag):
