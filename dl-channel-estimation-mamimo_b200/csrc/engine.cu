@@ -326,11 +326,8 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (LS) failed: " + std::to_string(r));
   constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES, NPS>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  // per launch, not cached in a static: the attribute is per device and a process may hold engines on several
+  CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int n_tiles = (a.n_sc + 63) / 64;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   const int per_sm = std::max(1, std::min(e->ls_tma_ctas, (227 * 1024) / (smem + 1024)));
@@ -623,8 +620,7 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
     b.cp_len = e->cp_len; b.sym_offset = e->sym_offset; b.n_sc = e->cfg.n_sc;
     b.total_syms = n_pkt * e->cfg.n_rx * e->cfg.n_ltf; b.x_double = 0; b.flags = e->d_flags;
     const unsigned grid = static_cast<unsigned>(std::min<long long>((b.total_syms + 15) / 16, static_cast<long long>(e->num_sms) * 3));
-    static bool set = false;
-    if (!set) { CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<8>())); set = true; }
+    CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<8>()));
     {
       ProfScope ps(e, st, kClsStage);
       ofdm_r16_tma_kernel<8><<<grid, 256, ofdm_r16_tma_smem<8>(), st>>>(b);
@@ -663,8 +659,7 @@ mamimo_status run_ofdm(mamimo_engine* e, const void* dx, int x_double, int64_t n
       ProfScope ps(e, st, kClsStage);
 #define OFDM_TMA_CASE(L)                                                                                              \
   {                                                                                                                   \
-    static bool set = false;                                                                                          \
-    if (!set) { CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<L>())); set = true; } \
+    CK(e, cudaFuncSetAttribute(ofdm_r16_tma_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ofdm_r16_tma_smem<L>())); \
     ofdm_r16_tma_kernel<L><<<pgrid, 256, ofdm_r16_tma_smem<L>(), st>>>(b);                                            \
   }
       switch (e->fft_len) {
