@@ -9,15 +9,16 @@ What is pinned here:
   2. inference.py's CSIPredictor.inference() executed unmodified, with a stub
      ``tensorflow.keras`` whose load_model() returns a deterministic numpy MLP
      (TensorFlow itself is not installed).  Pins pre/post-processing glue.
-  4. helperMIMOChannelEstimate.m and LMMSE_ce.m (MATLAB) executed UNMODIFIED by the MATLAB-subset interpreter
-     tests/golden/mini_matlab.py (MATLAB / Octave are not installed): LS estimate, ltf(ind), the isMMSE branch with
-     per-rx SNR, the data-phase case numSTS = 1, and LMMSE_ce called directly with Nps = 2.  helperGetP (a MathWorks
-     example helper that is not in the reference repo) is supplied as Sylvester-Hadamard.  Pins oracle.ls and
-     oracle.lmmse, and through them the CUDA path.
   3. massiveMIMO_dataGenerator.DataGenerator executed unmodified (stub
      ``tensorflow.keras.utils.Sequence``) on a synthetic pickle-shaped dataset
      built with create_massiveMIMO_CSIest_dnn_dataset.py:62's row formula.
      Pins per-pair input assembly and pair ordering.
+  4. helperMIMOChannelEstimate.m and LMMSE_ce.m (MATLAB) executed UNMODIFIED by the MATLAB-subset interpreter
+     tests/golden/mini_matlab.py (MATLAB / Octave are not installed): LS estimate, ltf(ind), the isMMSE branch with
+     per-rx SNR, the data-phase case numSTS = 1, and LMMSE_ce called directly with Nps = 2.  helperGetP (a MathWorks
+     example helper that is not in the reference repo) is supplied as Sylvester-Hadamard.  Pins oracle.ls and
+     oracle.lmmse, and through them the CUDA path.  Also NMSE_subk and the CSI(:,iTX,iRX) rebuild loop of
+     BER_test_maMIMO_LTF.m (:675-686, :213-218).
 
 Usage:  python tests/golden/make_golden.py   (writes next to this file)
 """
