@@ -60,3 +60,36 @@ def test_loop_form_equals_batched_form():
     ref = lmmse.helper_mmse_loop(hD, 1, tau, snr)                      # helperMIMOChannelEstimate.m:33-39 literal
     bat = lmmse.lmmse_batched(np.transpose(hD, (2, 1, 0))[None], lmmse.tau_rms(tau), snr[None], 1)[0]
     assert np.linalg.norm(np.transpose(bat, (2, 1, 0)) - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def _schur_cholesky(t):
+    """numpy statement of the generalised Schur algorithm exactly as csrc/lmmse.cuh's lmmse_schur_kernel runs it:
+    generator u = t / sqrt(t0), v = u with v0 = 0; step k emits column k of L, shifts u, applies the hyperbolic
+    rotation in mixed-downdating form."""
+    n = len(t)
+    u = (t / np.sqrt(t[0].real)).astype(np.complex128)
+    v = u.copy()
+    v[0] = 0
+    L = np.zeros((n, n), complex)
+    for k in range(n):
+        L[k:, k] = u[k:]
+        if k == n - 1:
+            break
+        u[k + 1:] = u[k:n - 1].copy()
+        rho = v[k + 1] / u[k + 1]
+        s = np.sqrt(1 - abs(rho) ** 2)
+        un = (u[k + 1:] - np.conj(rho) * v[k + 1:]) / s
+        v[k + 1:] = s * v[k + 1:] - rho * un
+        u[k + 1:] = un
+    return L
+
+
+@pytest.mark.parametrize("n,t_rms,snr_db,nps", [(234, 3.0, 10.0, 1), (100, 0.5, 30.0, 2), (64, 1e-7, 10.0, 1), (234, 5.0, 60.0, 1)])
+def test_schur_factorisation_is_a_backward_stable_cholesky_of_rpp(n, t_rms, snr_db, nps):
+    """Rpp of LMMSE_ce.m:35-38 is Hermitian Toeplitz, so the O(n^2) Schur recursion the CUDA path uses reproduces its
+    Cholesky factor: ||L L^H - Rpp|| / ||Rpp|| at rounding level even when cond(Rpp) ~ 1e8."""
+    _, Rpp = lmmse.correlation_matrices(n, n, nps, t_rms, snr_db)
+    assert np.allclose(Rpp[1:, 1:], Rpp[:-1, :-1], atol=0)                 # Toeplitz: constant along diagonals
+    L = _schur_cholesky(Rpp[:, 0].copy())
+    assert np.linalg.norm(L @ L.conj().T - Rpp) / np.linalg.norm(Rpp) < 1e-13
+    assert np.all(np.diag(L).real > 0) and np.allclose(np.triu(L, 1), 0)
