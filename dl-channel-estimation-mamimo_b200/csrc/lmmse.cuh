@@ -9,7 +9,12 @@
 //
 // The reference rebuilds and inverts the Nsc x Nsc matrix for every (tx, rx) pair; Rpp only depends on the packet
 // (tau_rms) and the rx antenna (SNR(i)), so one "slab" = (packet, rx) is ONE Hermitian positive-definite system
-// with the Nt LS vectors as right-hand sides.  Everything is FP64 (cond(Rpp) ~ Nsc * snr rules FP32 out):
+// with the Nt LS vectors as right-hand sides.  Everything is FP64 (cond(Rpp) ~ Nsc * snr rules FP32 out).
+//
+// Two routes share the workspace and the output formula:
+//   * Toeplitz route (default; further down: lmmse_schur / linv / solve kernels): Rpp is Hermitian Toeplitz, its
+//     Cholesky factor comes from the O(n^2) generalised Schur recursion, then two blocked triangular solves.
+//   * dense route (MAMIMO_LMMSE_SCHUR=0; the cross-check, described next): blocked left-looking Cholesky.
 //
 //   M = [ Rpp ; B^H ]   (n_pad + nt_pad) x n_pad, row-major double2, one per slab; its entries are generated on
 //   the fly (lm_elem), the buffer only ever holds the factor L and the solved right-hand sides
