@@ -9,7 +9,7 @@ import os
 from . import build as _build
 
 MAX_HIDDEN = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_RANGE, ERR_TIMEOUT = range(8)
 C64, C128 = 0, 1
@@ -50,7 +50,7 @@ SYMBOLS = [
     "mamimo_vht_ltf256", "mamimo_carriers_locations", "mamimo_default_p", "mamimo_pair_row",
     "mamimo_create", "mamimo_destroy", "mamimo_set_pilots", "mamimo_load_layer", "mamimo_finalize_weights",
     "mamimo_ls_estimate", "mamimo_estimate", "mamimo_estimate_stages", "mamimo_predict_planes", "mamimo_predict_time",
-    "mamimo_synchronize", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
+    "mamimo_synchronize", "mamimo_poll_flags", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end",
     "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time", "mamimo_lmmse", "mamimo_tau_rms",
     "mamimo_gather_create", "mamimo_gather_connect", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
@@ -85,6 +85,7 @@ def _load():
         "mamimo_predict_planes": (i32, [vp, vp, vp, i64, vp, vp, i32, vp]),
         "mamimo_predict_time": (i32, [vp, vp, vp, i64, vp, vp, i32, vp]),
         "mamimo_synchronize": (i32, [vp]),
+        "mamimo_poll_flags": (i32, [vp, vp]),
         "mamimo_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "mamimo_host_alloc": (vp, [C.c_size_t]),
         "mamimo_host_free": (None, [vp]),

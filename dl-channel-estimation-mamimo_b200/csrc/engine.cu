@@ -34,6 +34,7 @@ struct DevLayer {
   float* bias = nullptr;   // [N]
   int N = 0, K = 0;
   float w_scale = 1.f;
+  float rowsum = 0.f, bmax = 0.f;   // max_n sum_k |W[k][n]| and max_n |b[n]| of the folded layer (FP16X3 range bounds)
   CUtensorMap tmap_b;       // box of 256 weight rows (1-CTA kernel)
   CUtensorMap tmap_b_half;  // box of 128 weight rows (CTA-pair kernel: each CTA stages half the tile)
   CUtensorMap tmap_a;      // A operand of this layer (net-specific buffer for layer 0)
@@ -83,6 +84,12 @@ struct mamimo_engine {
   int n_layers = 0;             // n_hidden + 1 when an MLP is configured, else 0
   int elem_bytes = 4, planes = 1, block_k = 32;
   float act_scale = 1.f;
+  // FP16X3 range management (schemes.cuh): device-resolved per-level scales; dyn_fixed = act_scale_log2 pinned
+  DynState* d_dyn = nullptr;    // [kDynSlots]; slot = sub-batch in flight
+  bool dyn_fixed = false;
+  int dyn_slot = 0;
+  float ls_gain = 1.f;          // bound on |H_ls component| / amax |Y component|
+  float tmax[2] = {0.f, 0.f};   // mode A: max |T| of the de-duplicated first layer
   bool hadamard = false;
   bool finalized = false;
   std::vector<float> hP;        // [n_tx][n_ltf] complex interleaved
@@ -228,6 +235,34 @@ mamimo_status make_map(mamimo_engine* e, CUtensorMap* map, const Operand& op, in
 }
 
 constexpr int kTcBN = 256;
+constexpr int kDynSlots = 8;
+static_assert(kMaxLevels >= MAMIMO_MAX_HIDDEN + 1, "DynState levels");
+
+DynState* dyn_of(mamimo_engine* e) {
+  return (e->cfg.precision == MAMIMO_PREC_FP16X3 && e->d_dyn) ? e->d_dyn + e->dyn_slot : nullptr;
+}
+
+// start of a call's range bookkeeping: zero the slot, then (auto mode) the exact amax of the input planes
+mamimo_status dyn_begin(mamimo_engine* e, const void* in0, size_t n0, const void* in1, size_t n1, bool is_double,
+                        cudaStream_t st) {
+  DynState* d = dyn_of(e);
+  if (!d) return MAMIMO_OK;
+  CK(e, cudaMemsetAsync(d, 0, sizeof(DynState), st));
+  if (e->dyn_fixed) return MAMIMO_OK;
+  const void* ptr[2] = {in0, in1};
+  const size_t cnt[2] = {n0, n1};
+  for (int i = 0; i < 2; ++i) {
+    if (!ptr[i] || !cnt[i]) continue;
+    const size_t vec = cnt[i] / (is_double ? 2 : 4);
+    const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((vec + 255) / 256, static_cast<size_t>(e->num_sms) * 8)));
+    ProfScope ps(e, st, kClsStage);
+    if (is_double) amax_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(ptr[i]), cnt[i], &d->in_amax[i]);
+    else amax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(ptr[i]), cnt[i], &d->in_amax[i]);
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  return MAMIMO_OK;
+}
 
 template <int S>
 mamimo_status set_tc_attr(mamimo_engine* e) {
@@ -253,6 +288,15 @@ mamimo_status upload_layer(mamimo_engine* e, DevLayer& d, const std::vector<doub
   d.N = out; d.K = kpad;
   double wmax = 0;
   for (double v : Wf) wmax = std::max(wmax, std::fabs(v));
+  {
+    std::vector<double> colsum(out, 0.0);
+    for (int k = 0; k < in; ++k)
+      for (int n = 0; n < out; ++n) colsum[n] += std::fabs(Wf[static_cast<size_t>(k) * out + n]);
+    double rs = 0, bm = 0;
+    for (int n = 0; n < out; ++n) { rs = std::max(rs, colsum[n]); bm = std::max(bm, std::fabs(bf[n])); }
+    d.rowsum = static_cast<float>(rs * (1.0 + 1e-6));
+    d.bmax = static_cast<float>(bm * (1.0 + 1e-6));
+  }
   d.w_scale = 1.f;
   if (S == kFp16x3 && wmax > 0) {
     int ex;
@@ -423,6 +467,8 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
       a.flags = e->d_flags;
       a.l2_prefetch = e->l2_prefetch;
       a.dbg = e->d_dbg;
+      a.dyn = dyn_of(e); a.net = net; a.level = l; a.fixed_scale = e->dyn_fixed ? 1 : 0;
+      a.w_inv_scale = 1.0f / d.w_scale; a.rowsum = d.rowsum; a.bmax = d.bmax;
       a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
       if (last) {
         a.out_f32 = net == 0 ? out_r : out_i;
@@ -487,6 +533,7 @@ mamimo_status run_ls(mamimo_engine* e, const void* dY, int y_double, int n_pkt, 
   a.n_sc = e->cfg.n_sc; a.n_ps = e->cfg.n_ps; a.n_pil = e->n_pil;
   a.pil_per_tile = std::max(1, 128 / e->cfg.n_ps);
   a.y_double = y_double; a.h_double = h_double; a.flags = e->d_flags;
+  a.dyn = want_planes ? dyn_of(e) : nullptr; a.in_gain = e->ls_gain; a.fixed_scale = e->dyn_fixed ? 1 : 0;
   return launch_ls<S>(e, a, st);
 }
 
@@ -499,7 +546,8 @@ mamimo_status run_stage_planes(mamimo_engine* e, const float* dXr, const float* 
     const Operand& A = e->act_in[net];
     ProfScope ps(e, st, kClsStage);
     stage_planes_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dXr : dXi, A.ptr, rows, e->cfg.d_in, A.rows_alloc,
-                                                     A.kpad, e->act_scale, e->d_flags);
+                                                     A.kpad, e->act_scale, e->d_flags, dyn_of(e), net,
+                                                     e->dyn_fixed ? 1 : 0);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
   }
@@ -517,7 +565,7 @@ mamimo_status run_stage_time(mamimo_engine* e, const float* dSr, const float* dS
     ProfScope ps(e, st, kClsStage);
     stage_time_p_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dSr : dSi, e->dP, A.ptr, n_prx, e->cfg.n_tx,
                                                      e->cfg.n_ltf, e->cfg.len_ltf, A.rows_alloc, A.kpad,
-                                                     e->act_scale, e->d_flags);
+                                                     e->act_scale, e->d_flags, dyn_of(e), net, e->dyn_fixed ? 1 : 0);
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
   }
@@ -532,13 +580,16 @@ mamimo_status rebuild_mode_a_table(mamimo_engine* e) {
   if (e->hP.empty()) return fail(e, MAMIMO_ERR_STATE, "P not set (mamimo_set_pilots)");
   std::vector<float> T(static_cast<size_t>(nt) * h0);
   for (int net = 0; net < 2; ++net) {
+    double tm = 0;
     for (int j = 0; j < nt; ++j)
       for (int n = 0; n < h0; ++n) {
         double acc = e->hb0[net][n];
         for (int m = 0; m < nt; ++m)
           acc += static_cast<double>(e->hP[2 * (j * nl + m)]) * e->hW0p[net][static_cast<size_t>(m) * h0 + n];
         T[static_cast<size_t>(j) * h0 + n] = static_cast<float>(acc);
+        tm = std::max(tm, std::fabs(acc));
       }
+    e->tmax[net] = static_cast<float>(tm * (1.0 + 1e-6));
     CK(e, cudaMemcpy(e->d_T[net], T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   return MAMIMO_OK;
@@ -559,7 +610,8 @@ mamimo_status run_mode_a_dedup(mamimo_engine* e, const float* dSr, const float* 
       const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
       ProfScope ps(e, st, kClsStage);
       stage_planes_kernel<S><<<grid, threads, 0, st>>>(net == 0 ? dSr : dSi, A.ptr, n_prx, e->cfg.len_ltf, A.rows_alloc,
-                                                       A.kpad, e->act_scale, e->d_flags);
+                                                       A.kpad, e->act_scale, e->d_flags, dyn_of(e), net,
+                                                       e->dyn_fixed ? 1 : 0);
     }
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
@@ -570,6 +622,8 @@ mamimo_status run_mode_a_dedup(mamimo_engine* e, const float* dSr, const float* 
     a.a_plane_rows = A.rows_alloc; a.b_plane_rows = d.w.rows_alloc;
     a.bias = d.bias; a.alpha = 1.0f / (e->act_scale * d.w_scale); a.relu = 0;
     a.flags = e->d_flags; a.dbg = e->d_dbg;
+    a.dyn = dyn_of(e); a.net = net; a.level = 0; a.fixed_scale = e->dyn_fixed ? 1 : 0;
+    a.w_inv_scale = 1.0f / d.w_scale; a.rowsum = d.rowsum; a.bmax = d.bmax;
     a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
     a.out_f32 = e->d_z[net]; a.out_ld = h0;
     mamimo_status s = launch_fc<S>(e, d, a, st);
@@ -580,7 +634,8 @@ mamimo_status run_mode_a_dedup(mamimo_engine* e, const float* dSr, const float* 
       const int grid = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, e->num_sms * 16));
       ProfScope ps(e, st, kClsStage);
       expand_pairs_kernel<S><<<grid, threads, 0, st>>>(e->d_z[net], e->d_T[net], O.ptr, n_prx, e->cfg.n_tx, h0,
-                                                       O.rows_alloc, e->dl[net][1].K, e->act_scale, e->d_flags);
+                                                       O.rows_alloc, e->dl[net][1].K, e->act_scale, e->d_flags,
+                                                       dyn_of(e), net, e->dyn_fixed ? 1 : 0, d.rowsum, e->tmax[net]);
     }
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
@@ -726,7 +781,8 @@ mamimo_status check_flags(mamimo_engine* e, cudaStream_t st) {
   if (f) {
     CK(e, cudaMemsetAsync(e->d_flags, 0, sizeof(uint32_t), st));
     if (f & kFlagTimeout) return fail(e, MAMIMO_ERR_TIMEOUT, "device pipeline wait timed out (kernel aborted)");
-    if (f & kFlagRange) return fail(e, MAMIMO_ERR_RANGE, "fp16 split operand overflow: lower act_scale_log2 or use TF32X3");
+    if (f & kFlagRange) return fail(e, MAMIMO_ERR_RANGE, "fp16 split operand overflow (non-finite input, or a pinned act_scale_log2 too high): use act_scale_log2 = 0 (auto) or TF32X3");
+    if (f & kFlagUnderflow) return fail(e, MAMIMO_ERR_RANGE, "fp16 split operand below the accuracy window of the pinned act_scale_log2: use act_scale_log2 = 0 (auto) or TF32X3");
     if (f & kFlagNotPd) return fail(e, MAMIMO_ERR_RANGE, "LMMSE: Rpp is not positive definite in FP64 (SNR too high for this tau_rms)");
   }
   return MAMIMO_OK;
@@ -849,7 +905,7 @@ void mamimo_config_init(mamimo_config* c) {
   c->n_ps = 1;
   c->precision = MAMIMO_PREC_TF32X3;
   c->input_mode = MAMIMO_INPUT_LS;
-  c->act_scale_log2 = 6;
+  c->act_scale_log2 = 0;   /* auto */
 }
 
 void mamimo_vht_ltf256(int8_t out[256]) {
@@ -933,8 +989,9 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
     case MAMIMO_PREC_FP16X3: e->elem_bytes = 2; e->planes = 2; e->block_k = Scheme<kFp16x3>::kBlockK; break;
     default: e->elem_bytes = 2; e->planes = 1; e->block_k = Scheme<kBf16x1>::kBlockK; break;
   }
-  e->act_scale = (cfg->precision == MAMIMO_PREC_FP16X3)
-                     ? std::ldexp(1.0f, cfg->act_scale_log2 ? cfg->act_scale_log2 : 6) : 1.0f;
+  e->dyn_fixed = cfg->precision == MAMIMO_PREC_FP16X3 && cfg->act_scale_log2 != 0;
+  if (cfg->act_scale_log2 < -60 || cfg->act_scale_log2 > 60) { e->err = "act_scale_log2 out of range [-60, 60]"; return bail(MAMIMO_ERR_INVALID); }
+  e->act_scale = e->dyn_fixed ? std::ldexp(1.0f, cfg->act_scale_log2) : 1.0f;
 
   // chunking: ~64K rows per chunk by default
   int rows_per_unit = cfg->input_mode == MAMIMO_INPUT_PLANES ? 1 : e->rows_per_pkt;
@@ -966,6 +1023,10 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   auto ck = [&](cudaError_t ce, const char* what) { if (ce != cudaSuccess && s == MAMIMO_OK) s = fail_cuda(e, ce, what); };
   ck(cudaMalloc(&e->d_flags, sizeof(uint32_t)), "cudaMalloc flags");
   if (s == MAMIMO_OK) ck(cudaMemset(e->d_flags, 0, sizeof(uint32_t)), "memset flags");
+  if (cfg->precision == MAMIMO_PREC_FP16X3) {
+    ck(cudaMalloc(&e->d_dyn, kDynSlots * sizeof(DynState)), "cudaMalloc dyn");
+    if (s == MAMIMO_OK) ck(cudaMemset(e->d_dyn, 0, kDynSlots * sizeof(DynState)), "memset dyn");
+  }
   ck(cudaMallocHost(&e->h_flags, sizeof(uint32_t)), "cudaMallocHost flags");
   ck(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking), "stream");
   ck(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking), "stream");
@@ -1039,7 +1100,7 @@ void mamimo_destroy(mamimo_engine* e) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_dyn); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -1080,12 +1141,25 @@ mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const fl
   }
   e->hadamard = is_sylvester(e->hP, nt, nl);
   std::vector<float> inv(static_cast<size_t>(2) * e->n_pil);
+  double inv_max = 0;
   for (int i = 0; i < e->n_pil; ++i) {
     const double xr = x_pilot ? x_pilot[2 * i] : 1.0, xi = x_pilot ? x_pilot[2 * i + 1] : 0.0;
     const double den = (xr * xr + xi * xi) * nl;
     if (den == 0.0) return fail(e, MAMIMO_ERR_INVALID, "pilot tone " + std::to_string(i) + " is zero");
     inv[2 * i] = static_cast<float>(xr / den);          // 1/(nl*x) = conj(x)/(nl*|x|^2)
     inv[2 * i + 1] = static_cast<float>(-xi / den);
+    inv_max = std::max(inv_max, std::sqrt(xr * xr + xi * xi) / den);
+  }
+  {
+    // |H component| <= |H| <= sum_n |Y_n| |P[j][n]| |inv| <= sqrt(2) amax|Y comp| * max_j sum_n |P[j][n]| * max |inv|;
+    // comb pilots: the last segment extrapolates by at most one pilot spacing (|h0 + w (h1 - h0)|, w < 2)
+    double prow = 0;
+    for (int j = 0; j < nt; ++j) {
+      double r = 0;
+      for (int n = 0; n < nl; ++n) r += std::hypot(e->hP[2 * (j * nl + n)], e->hP[2 * (j * nl + n) + 1]);
+      prow = std::max(prow, r);
+    }
+    e->ls_gain = static_cast<float>(1.41421357 * prow * inv_max * (e->cfg.n_ps > 1 ? 5.0 : 1.0) * (1.0 + 1e-5));
   }
   if (!e->dP) CK(e, cudaMalloc(&e->dP, e->hP.size() * sizeof(float)));
   if (!e->d_inv_den) CK(e, cudaMalloc(&e->d_inv_den, inv.size() * sizeof(float)));
@@ -1223,8 +1297,12 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
     mamimo_status s = MAMIMO_OK;
-    if (stages & MAMIMO_STAGE_LS)
+    if (stages & MAMIMO_STAGE_LS) {
+      s = dyn_begin(e, in0, static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
+                    y_type == MAMIMO_C128, st);
+      if (s != MAMIMO_OK) return s;
       s = DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, 0, true, st)));
+    }
     if (s != MAMIMO_OK) return s;
     const unsigned nets = (stages >> 1) & 3u;
     if (!nets) return s;
@@ -1313,7 +1391,10 @@ mamimo_status mamimo_predict_planes(mamimo_engine* e, const float* X_real, const
   const size_t xb = static_cast<size_t>(e->cfg.d_in) * sizeof(float);
   const size_t hb = static_cast<size_t>(e->cfg.d_out) * sizeof(float);
   auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
-    mamimo_status s = DISPATCH_S(e, (run_stage_planes<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
+    const size_t cnt = static_cast<size_t>(n) * e->cfg.d_in;
+    mamimo_status s = dyn_begin(e, in0, cnt, in1, cnt, false, st);
+    if (s != MAMIMO_OK) return s;
+    s = DISPATCH_S(e, (run_stage_planes<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
     if (s != MAMIMO_OK) return s;
     return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n), hr, hi, st)));
   };
@@ -1331,9 +1412,19 @@ mamimo_status mamimo_predict_time(mamimo_engine* e, const float* sig_real, const
   const size_t xb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.len_ltf * sizeof(float);
   const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
   auto stage = [&](int64_t n, const void* in0, const void* in1, void*, float* hr, float* hi, cudaStream_t st) {
+    const size_t cnt = static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.len_ltf;
+    mamimo_status s = dyn_begin(e, in0, cnt, in1, cnt, false, st);
+    if (s != MAMIMO_OK) return s;
     if (e->dedup_a)
       return DISPATCH_S(e, (run_mode_a_dedup<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, hr, hi, st)));
-    mamimo_status s = DISPATCH_S(e, (run_stage_time<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
+    if (DynState* d = dyn_of(e); d && !e->dyn_fixed) {      // the P-row columns of the input belong to its range too
+      for (int net = 0; net < 2; ++net)
+        amax_kernel<float><<<1, 256, 0, st>>>(reinterpret_cast<const float*>(e->dP),
+                                              static_cast<size_t>(2) * e->cfg.n_tx * e->cfg.n_ltf, &d->in_amax[net]);
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches += 2;
+    }
+    s = DISPATCH_S(e, (run_stage_time<S>(e, static_cast<const float*>(in0), static_cast<const float*>(in1), n, st)));
     if (s != MAMIMO_OK) return s;
     return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
   };
@@ -1514,6 +1605,11 @@ mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
     mamimo_status s = run_ofdm(e, in0, x_type == MAMIMO_C128, n, e->d_ydemod, st);
     if (s != MAMIMO_OK) return s;
+    if (mlp) {
+      s = dyn_begin(e, e->d_ydemod, static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
+                    false, st);
+      if (s != MAMIMO_OK) return s;
+    }
     s = DISPATCH_S(e, (run_ls<S>(e, e->d_ydemod, 0, static_cast<int>(n), hls, 0, mlp, st)));
     if (s != MAMIMO_OK || !mlp) return s;
     return DISPATCH_S(e, (run_mlp_both<S>(e, static_cast<int>(n) * e->rows_per_pkt, hr, hi, st)));
@@ -1708,6 +1804,12 @@ mamimo_status mamimo_synchronize(mamimo_engine* e) {
   CK(e, cudaSetDevice(e->cfg.device));
   CK(e, cudaDeviceSynchronize());
   return check_flags(e, e->s_comp);
+}
+
+mamimo_status mamimo_poll_flags(mamimo_engine* e, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  CK(e, cudaSetDevice(e->cfg.device));
+  return check_flags(e, static_cast<cudaStream_t>(stream));
 }
 
 mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out) {

@@ -60,7 +60,41 @@ struct FcArgs {
   int gather_world;      // fused all-gather (pair kernel, final layer): ranks to store to
   int l2_prefetch;       // pair kernel: prefetch the next tile's activation rows into L2
   unsigned long long* dbg;  // optional [8]: cycles the pair kernel's roles spent waiting (MAMIMO_FC_DEBUG=1)
+  // FP16X3 range management (schemes.cuh).  dyn != nullptr: alpha = w_inv_scale / dyn->scale[net][level]; a hidden
+  // layer picks its output scale from |out| <= rowsum * amax(level) + bmax (or keeps out_scale when fixed_scale),
+  // publishes it as dyn->scale[net][level + 1] and the measured amax of its outputs as dyn->amax[net][level + 1].
+  DynState* dyn;
+  int net, level, fixed_scale;
+  float w_inv_scale;     // 1 / weight scale
+  float rowsum;          // max_n sum_k |W[k][n]| (BN-folded), rounded up
+  float bmax;            // max_n |bias[n]|
 };
+
+struct FcScales {
+  float alpha, out_scale;
+};
+
+// every epilogue thread resolves the same two numbers (two broadcast loads from L2); `writer` is one thread of the
+// grid, which publishes the output scale and runs the pinned-scale window check
+template <int S>
+__device__ __forceinline__ FcScales fc_resolve_scales(const FcArgs& a, bool writer) {
+  FcScales r{a.alpha, a.out_scale};
+  if constexpr (S == kFp16x3) {
+    if (a.dyn) {
+      const float s_in = a.dyn->scale[a.net][a.level];
+      const float amax_in = __uint_as_float(a.dyn->amax[a.net][a.level]);
+      r.alpha = a.w_inv_scale / s_in;                     // powers of two: exact
+      if (a.out_planes) {
+        if (!a.fixed_scale) r.out_scale = pow2_scale_for(fmaf(a.rowsum, amax_in, a.bmax));
+        if (writer) a.dyn->scale[a.net][a.level + 1] = r.out_scale;
+      }
+      // pinned scale: the consumer of a level checks that the level sat inside the accuracy window
+      if (a.fixed_scale && writer && amax_in > 0.f && amax_in * s_in < 1.0f)
+        atomicOr(a.flags, kFlagUnderflow);
+    }
+  }
+  return r;
+}
 
 constexpr int kFcBlockM = 128;
 // warpgroup 0: warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2-3 idle (donate registers)
@@ -86,34 +120,38 @@ struct FcTcCfg {
 };
 
 // One 32-column group of one row: bias, activation, then either split planes or float32.
-template <int S>
-__device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const float (&acc)[32], const float* sbias,
-                                                  int row, int n0, bool& ovf) {
+template <int S, bool kTrack = true>
+__device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const FcScales& sc, const float (&acc)[32],
+                                                  const float* sbias, int row, int n0, bool& ovf, float& amx) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float x = fmaf(acc[j], a.alpha, sbias[j]);
+    float x = fmaf(acc[j], sc.alpha, sbias[j]);
     if (a.relu) x = fmaxf(x, 0.0f);
     v[j] = x;
   }
   if (a.out_planes) {
     if (n0 >= a.out_kpad) return;
+    if constexpr (S == kFp16x3 && kTrack) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) amx = fmaxf(amx, fabsf(v[j]));
+    }
     constexpr int kWords = 32 * sizeof(E) / 4;            // 32-bit words per plane per group
     uint32_t pk[Sch::kPlanes][kWords];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       if constexpr (S == kFp16x3) {
         uint32_t w[2];
-        Sch::split2(v[j], v[j + 1], a.out_scale, w, &ovf);
+        Sch::split2(v[j], v[j + 1], sc.out_scale, w, &ovf);
         pk[0][j >> 1] = w[0];
         pk[1][j >> 1] = w[1];
         continue;
       }
       E p0[Sch::kPlanes], p1[Sch::kPlanes];
-      Sch::split(v[j], a.out_scale, p0, &ovf);
-      Sch::split(v[j + 1], a.out_scale, p1, &ovf);
+      Sch::split(v[j], sc.out_scale, p0, &ovf);
+      Sch::split(v[j + 1], sc.out_scale, p1, &ovf);
 #pragma unroll
       for (int q = 0; q < Sch::kPlanes; ++q) {
         if constexpr (sizeof(E) == 4) {
@@ -276,6 +314,8 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int half = ew >> 2;                       // column half
     const int et = ew * 32 + lane;                  // 0..255 among epilogue threads
     bool ovf = false;
+    float amx = 0.f;
+    const FcScales sc = fc_resolve_scales<S>(a, blockIdx.x == 0 && threadIdx.x == kFcThreads - kFcEpiThreads);
     uint32_t unit = 0;
     int it = 0;
     bool ok = true;
@@ -316,11 +356,12 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
           const int col = half * Cfg::kColsPerThread + g * 32;
-          fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+          fc_epilogue_chunk<S>(a, sc, sum[g], sb + col, row, n_blk * BN + col, ovf, amx);
         }
       }
     }
     if (ovf) atomicOr(a.flags, kFlagRange);
+    if (a.out_planes) publish_amax<S>(a.dyn, a.net, a.level + 1, amx);
   }
 
   tc_fence_before_sync();
@@ -529,6 +570,8 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     const int half = ew >> 2;
     const int et = ew * 32 + lane;
     bool ovf = false;
+    float amx = 0.f;
+    const FcScales sc = fc_resolve_scales<S>(a, blockIdx.x == 0 && threadIdx.x == kFcThreads - kFcEpiThreads);
     uint32_t unit = 0;
     int it = 0;
     bool ok = true;
@@ -571,7 +614,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < kGroups; ++g) {
             const int col = half * Cfg::kColsPerThread + g * 32;
-            fc_epilogue_chunk<S>(a, sum[g], sb + col, row, n_blk * BN + col, ovf);
+            fc_epilogue_chunk<S, !kGather>(a, sc, sum[g], sb + col, row, n_blk * BN + col, ovf, amx);
           }
         }
       }
@@ -587,10 +630,10 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                     // 8 x 16 B per row, SWIZZLE_128B placement
             float4 v;
-            v.x = fmaf(sum[g][4 * c + 0], a.alpha, sb[col + 4 * c + 0]);
-            v.y = fmaf(sum[g][4 * c + 1], a.alpha, sb[col + 4 * c + 1]);
-            v.z = fmaf(sum[g][4 * c + 2], a.alpha, sb[col + 4 * c + 2]);
-            v.w = fmaf(sum[g][4 * c + 3], a.alpha, sb[col + 4 * c + 3]);
+            v.x = fmaf(sum[g][4 * c + 0], sc.alpha, sb[col + 4 * c + 0]);
+            v.y = fmaf(sum[g][4 * c + 1], sc.alpha, sb[col + 4 * c + 1]);
+            v.z = fmaf(sum[g][4 * c + 2], sc.alpha, sb[col + 4 * c + 2]);
+            v.w = fmaf(sum[g][4 * c + 3], sc.alpha, sb[col + 4 * c + 3]);
             if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             *reinterpret_cast<float4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
           }
@@ -607,6 +650,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       if (q == 0 && lane == 0) tma_store_wait_all<0>();     // every peer write has left before the CTA retires
     }
     if (ovf) atomicOr(a.flags, kFlagRange);
+    if constexpr (!kGather) { if (a.out_planes) publish_amax<S>(a.dyn, a.net, a.level + 1, amx); }
   }
 
   tc_fence_before_sync();

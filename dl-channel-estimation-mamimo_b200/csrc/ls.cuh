@@ -33,7 +33,25 @@ struct LsArgs {
   int pil_per_tile;       // pilots per CTA
   int y_double, h_double;
   uint32_t* flags;
+  // FP16X3 range management (schemes.cuh): scale resolved on the device from dyn->in_amax[0] * in_gain unless
+  // fixed_scale; the kernel publishes the scale it used and the measured amax of both planes as level 0
+  DynState* dyn;
+  float in_gain;          // bound on |H component| / amax|Y component| (P row sums, 1/|nltf x|, interpolation)
+  int fixed_scale;
 };
+
+template <int S>
+__device__ __forceinline__ float ls_resolve_scale(const LsArgs& a) {
+  if constexpr (S == kFp16x3) {
+    if (a.dyn && a.planes[0]) {
+      const float s = a.fixed_scale ? a.scale : pow2_scale_for(a.in_gain * __uint_as_float(a.dyn->in_amax[0]));
+      if (blockIdx.x == 0 && threadIdx.x == 0) { a.dyn->scale[0][0] = s; a.dyn->scale[1][0] = s; }
+      return s;
+    }
+  }
+  return a.scale;
+}
+
 
 template <int NLTF>
 __device__ __forceinline__ void fwht(float2 (&v)[NLTF]) {
@@ -66,7 +84,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // 8/16/32-byte stores
 template <int S>
 __device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, const float (&re)[4], const float (&im)[4],
-                                          bool& ovf) {
+                                          bool& ovf, float (&amx)[2]) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   if (a.H_ls) {
@@ -82,6 +100,8 @@ __device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, co
   }
   if (a.planes[0]) {
     if constexpr (S == kFp16x3) {
+      amx[0] = fmaxf(amx[0], fmaxf(fmaxf(fabsf(re[0]), fabsf(re[1])), fmaxf(fabsf(re[2]), fabsf(re[3]))));
+      amx[1] = fmaxf(amx[1], fmaxf(fmaxf(fabsf(im[0]), fabsf(im[1])), fmaxf(fabsf(im[2]), fabsf(im[3]))));
       uint32_t r01[2], r23[2], i01[2], i23[2];
       Sch::split2(re[0], re[1], a.scale, r01, &ovf);
       Sch::split2(re[2], re[3], a.scale, r23, &ovf);
@@ -123,7 +143,8 @@ __device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, co
 // Phase 2 of the LS kernels: the CTA sweeps (tx, k) of its tile with k fastest, interpolates between pilots when
 // n_ps > 1 (n_ps == 1 is a pure copy: bit-exact identity) and writes H_ls and the split operand planes.
 template <int S>
-__device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int pitch, int prx, int pil0, int lo) {
+__device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int pitch, int prx, int pil0, int lo,
+                                        float (&amx)[2]) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   // ---- phase 2: interpolate + emit ------------------------------------------------------
@@ -144,7 +165,7 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
       const float4 v23 = *reinterpret_cast<const float4*>(sh + j * pitch + kk + 2);
       const float re[4] = {v01.x, v01.z, v23.x, v23.z};
       const float im[4] = {v01.y, v01.w, v23.y, v23.w};
-      ls_store4<S>(a, row0 + j, k0 + kk, re, im, ovf);
+      ls_store4<S>(a, row0 + j, k0 + kk, re, im, ovf, amx);
     }
   } else {
     const float inv_nps = 1.0f / static_cast<float>(a.n_ps);
@@ -169,6 +190,8 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
         else reinterpret_cast<float2*>(a.H_ls)[row * a.n_sc + k] = h;
       }
       if (a.planes[0]) {
+        amx[0] = fmaxf(amx[0], fabsf(h.x));
+        amx[1] = fmaxf(amx[1], fabsf(h.y));
         E pr[Sch::kPlanes], pi[Sch::kPlanes];
         Sch::split(h.x, a.scale, pr, &ovf);
         Sch::split(h.y, a.scale, pi, &ovf);
@@ -188,10 +211,12 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
 // matvec against P (shared memory); NLTF > 0 unrolls it over registers, NLTF == 0 is the any-size
 // (n_ltf <= 64) fallback.
 template <int S, int NLTF, bool HAD>
-__global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
+__global__ void __launch_bounds__(128) ls_kernel(const LsArgs a_in) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   extern __shared__ float2 sm_ls[];
+  LsArgs a = a_in;
+  a.scale = ls_resolve_scale<S>(a_in);
   const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
   const int tile = blockIdx.x % n_tiles;
   const int prx = blockIdx.x / n_tiles;                 // pkt * n_rx + rx
@@ -271,7 +296,9 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a) {
   }
   __syncthreads();
 
-  ls_emit<S>(a, sh, pitch, prx, pil0, lo);
+  float amx[2] = {0.f, 0.f};
+  ls_emit<S>(a, sh, pitch, prx, pil0, lo, amx);
+  if (a.planes[0]) { publish_amax<S>(a.dyn, 0, 0, amx[0]); publish_amax<S>(a.dyn, 1, 0, amx[1]); }
 }
 
 // Hadamard despread with the transform split over threads (n_ps == 1, NLTF = 32 or 64): a CTA owns 64 tones;
@@ -318,7 +345,10 @@ __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsA
   __syncthreads();
   LsArgs a2 = a;
   a2.pil_per_tile = T;
-  ls_emit<S>(a2, sh, pitch, prx, pil0, pil0);
+  a2.scale = ls_resolve_scale<S>(a);
+  float amx[2] = {0.f, 0.f};
+  ls_emit<S>(a2, sh, pitch, prx, pil0, pil0, amx);
+  if (a.planes[0]) { publish_amax<S>(a.dyn, 0, 0, amx[0]); publish_amax<S>(a.dyn, 1, 0, amx[1]); }
 }
 
 // Persistent TMA-fed variant of ls_had_split_kernel (complex64 Y, n_ps == 1, NLTF = 32 or 64): the [NLTF x 64 tones]
@@ -368,6 +398,8 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
   const int b = threadIdx.x / T;
   LsArgs a2 = a;
   a2.pil_per_tile = T;
+  a2.scale = ls_resolve_scale<S>(a);
+  float amx[2] = {0.f, 0.f};
   long long it = 0;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int stage = static_cast<int>(it % STAGES);
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
     }
     __syncthreads();
     if constexpr (NPS == 1) {
-      ls_emit<S>(a2, sh, TW, prx, pil0, pil0);
+      ls_emit<S>(a2, sh, TW, prx, pil0, pil0, amx);
     } else {
       const int k0 = tl * T;
       const int nk = min(T, a.n_sc - k0);
@@ -425,7 +457,7 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
           re[i] = h0.x + w * (h1.x - h0.x);
           im[i] = h0.y + w * (h1.y - h0.y);
         }
-        ls_store4<S>(a, row0 + j, k0 + kk, re, im, ovf);
+        ls_store4<S>(a2, row0 + j, k0 + kk, re, im, ovf, amx);
       }
       if (ovf) atomicOr(a.flags, kFlagRange);
     }
@@ -438,27 +470,39 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
       }
     }
   }
+  if (a.planes[0]) { publish_amax<S>(a.dyn, 0, 0, amx[0]); publish_amax<S>(a.dyn, 1, 0, amx[1]); }
 }
 
 // ---- mode B: caller planes float32 [rows][d_in] -> operand planes (inference.py:29-30) ----
 template <int S>
 __global__ void stage_planes_kernel(const float* __restrict__ X, void* planes, int64_t rows, int d_in,
-                                    int plane_rows, int kpad, float scale, uint32_t* flags) {
+                                    int plane_rows, int kpad, float scale, uint32_t* flags, DynState* dyn, int net,
+                                    int fixed_scale) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   bool ovf = false;
+  float amx = 0.f;
+  if constexpr (S == kFp16x3) {
+    if (dyn) {      // level 0 of `net`: exact amax of this plane from the pre-pass (schemes.cuh)
+      if (!fixed_scale) scale = pow2_scale_for(__uint_as_float(dyn->in_amax[net]));
+      if (blockIdx.x == 0 && threadIdx.x == 0) dyn->scale[net][0] = scale;
+    }
+  }
   const int64_t total = rows * d_in;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / d_in;
     const int c = static_cast<int>(i - r * d_in);
     E p[Sch::kPlanes];
-    Sch::split(__ldg(X + i), scale, p, &ovf);
+    const float x = __ldg(X + i);
+    amx = fmaxf(amx, fabsf(x));
+    Sch::split(x, scale, p, &ovf);
 #pragma unroll
     for (int pl = 0; pl < Sch::kPlanes; ++pl)
       reinterpret_cast<E*>(planes)[(static_cast<size_t>(pl) * plane_rows + r) * kpad + c] = p[pl];
   }
   if (ovf) atomicOr(flags, kFlagRange);
+  publish_amax<S>(dyn, net, 0, amx);
 }
 
 // ---- mode A: [time-domain LTF || P(:,iTx)] per pair (massiveMIMO_dataGenerator.py:303-316) ----
@@ -466,10 +510,17 @@ __global__ void stage_planes_kernel(const float* __restrict__ X, void* planes, i
 template <int S>
 __global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2* __restrict__ P, void* planes,
                                     int64_t n_prx, int n_tx, int n_ltf, int len_ltf, int plane_rows, int kpad,
-                                    float scale, uint32_t* flags) {
+                                    float scale, uint32_t* flags, DynState* dyn, int net, int fixed_scale) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   bool ovf = false;
+  float amx = 0.f;
+  if constexpr (S == kFp16x3) {
+    if (dyn) {      // in_amax[net] was seeded with max |Re P| before the pre-pass over the signal plane
+      if (!fixed_scale) scale = pow2_scale_for(__uint_as_float(dyn->in_amax[net]));
+      if (blockIdx.x == 0 && threadIdx.x == 0) dyn->scale[net][0] = scale;
+    }
+  }
   const int d_in = len_ltf + n_tx;
   const int64_t total = n_prx * n_tx * d_in;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -479,6 +530,7 @@ __global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2*
     const int64_t prx = r / n_tx;
     const int j = static_cast<int>(r - prx * n_tx);
     const float x = (c < len_ltf) ? __ldg(sig + prx * len_ltf + c) : P[j * n_ltf + (c - len_ltf)].x;
+    amx = fmaxf(amx, fabsf(x));
     E p[Sch::kPlanes];
     Sch::split(x, scale, p, &ovf);
 #pragma unroll
@@ -486,6 +538,7 @@ __global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2*
       reinterpret_cast<E*>(planes)[(static_cast<size_t>(pl) * plane_rows + r) * kpad + c] = p[pl];
   }
   if (ovf) atomicOr(flags, kFlagRange);
+  publish_amax<S>(dyn, net, 0, amx);
 }
 
 // ---- mode A, de-duplicated first layer --------------------------------------------------------------------
@@ -497,10 +550,18 @@ __global__ void stage_time_p_kernel(const float* __restrict__ sig, const float2*
 template <int S>
 __global__ void expand_pairs_kernel(const float* __restrict__ Z, const float* __restrict__ T, void* planes,
                                     int64_t n_prx, int n_tx, int h, int plane_rows, int kpad, float scale,
-                                    uint32_t* flags) {
+                                    uint32_t* flags, DynState* dyn, int net, int fixed_scale, float rowsum,
+                                    float tmax) {
   using Sch = Scheme<S>;
   using E = typename Sch::elem;
   bool ovf = false;
+  float amx = 0.f;
+  if constexpr (S == kFp16x3) {
+    if (dyn) {      // level 1: |relu(Z + T)| <= rowsum(W1_ltf) * amax(level 0) + max |T|
+      if (!fixed_scale) scale = pow2_scale_for(fmaf(rowsum, __uint_as_float(dyn->amax[net][0]), tmax));
+      if (blockIdx.x == 0 && threadIdx.x == 0) dyn->scale[net][1] = scale;
+    }
+  }
   const int hq = kpad >> 2;                                // h % 4 == 0 (checked on the host); pad columns get zeros
   const int64_t total = n_prx * n_tx * hq;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -515,6 +576,7 @@ __global__ void expand_pairs_kernel(const float* __restrict__ Z, const float* __
       t = __ldg(reinterpret_cast<const float4*>(T + static_cast<size_t>(j) * h + n));
     }
     const float v[4] = {fmaxf(z.x + t.x, 0.f), fmaxf(z.y + t.y, 0.f), fmaxf(z.z + t.z, 0.f), fmaxf(z.w + t.w, 0.f)};
+    amx = fmaxf(amx, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
     E p[4][Sch::kPlanes];
 #pragma unroll
     for (int q = 0; q < 4; ++q) Sch::split(v[q], scale, p[q], &ovf);
@@ -531,6 +593,28 @@ __global__ void expand_pairs_kernel(const float* __restrict__ Z, const float* __
     }
   }
   if (ovf) atomicOr(flags, kFlagRange);
+  publish_amax<S>(dyn, net, 1, amx);
+}
+
+// ---- amax pre-pass of the FP16X3 range management: max |component| of a float / double array ----------------
+template <typename T>
+__global__ void __launch_bounds__(256) amax_kernel(const T* __restrict__ p, size_t n, uint32_t* out_bits) {
+  constexpr int V = 16 / sizeof(T);                      // elements per 16-byte load
+  float m = 0.f;
+  const size_t nv = n / V;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv; i += stride) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    } else {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(p) + i);
+      m = fmaxf(m, fmaxf(fabsf(static_cast<float>(v.x)), fabsf(static_cast<float>(v.y))));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * V) m = fmaxf(m, fabsf(static_cast<float>(p[nv * V + threadIdx.x])));
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && w) atomicMax(out_bits, w);
 }
 
 }  // namespace mm

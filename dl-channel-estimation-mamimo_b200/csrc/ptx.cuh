@@ -11,6 +11,7 @@ namespace mm {
 // device-visible error flags (mamimo_stats.last_device_flags)
 constexpr uint32_t kFlagRange = 1u;
 constexpr uint32_t kFlagTimeout = 2u;
+constexpr uint32_t kFlagUnderflow = 8u;   // fixed-scale FP16X3 operand level below the accuracy window (bit 2 = LMMSE not-PD)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

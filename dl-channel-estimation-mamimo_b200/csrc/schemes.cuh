@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace mm {
 
@@ -123,6 +124,58 @@ struct Scheme<kBf16x1> {
 // (A plane, B plane) of pass i -- smallest terms last so the dominant product opens the accumulator
 __host__ __device__ constexpr int pass_a(int i) { return i == 2 ? 1 : 0; }
 __host__ __device__ constexpr int pass_b(int i) { return i == 1 ? 1 : 0; }
+
+// ---- range management of the FP16X3 scheme ------------------------------------------------------------
+// fp16 hi+lo planes carry ~22 bits only while the scaled values sit inside fp16's normal range: the residual
+// plane goes subnormal (absolute error 2^-25 in scaled units) once |x|*scale drops below ~2^-2, and anything
+// above 65504 overflows.  So the operand scale of every activation level is a power of two chosen ON THE
+// DEVICE, per call, from a bound on that level's largest magnitude:
+//   level 0 (net input)      : exact amax of the caller's input (one streaming pre-pass) x the LS gain
+//   level l+1 (hidden layer) : max_n sum_k |W_l[k][n]| * amax(level l, measured by its producer) + max |b_l|
+// which puts the level's amax in [2^7, 2^15) scaled (bound looseness <= K) and leaves >= 10 binades below the
+// typical row before a weak row loses relative accuracy.  Powers of two make the scaling itself exact.
+// act_scale_log2 != 0 pins one fixed scale instead (no pre-pass); then overflow AND underflow are flagged.
+constexpr int kMaxLevels = 9;            // activation levels per net: input of layer 0 .. input of layer 8
+struct DynState {
+  uint32_t in_amax[2];                   // float bits: amax of the raw input feeding net 0 / net 1 (LS: [0] only)
+  uint32_t pad[2];
+  uint32_t amax[2][kMaxLevels];          // float bits: measured amax of the level's (unscaled) activations
+  float scale[2][kMaxLevels];            // scale the level's operand planes were written with
+};
+
+// largest power of two s <= 2^60 with bound * s < 2^15 (fp16 max is ~2^16: one binade of rounding headroom)
+__host__ __device__ inline float pow2_scale_for(float bound) {
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(bound);
+#else
+  memcpy(&u, &bound, 4);
+#endif
+  uint32_t e = (u >> 23) & 0xffu;        // bound in [2^(e-127), 2^(e-126))
+  if (e == 0xffu) e = 0xfeu;             // inf / nan: the split flags the overflow
+  if (e < 81u) e = 81u;                  // bound < 2^-46 (incl. 0): cap the scale at 2^60
+  u = (268u - e) << 23;                  // 2^(141 - e)
+  float s;
+#ifdef __CUDA_ARCH__
+  s = __uint_as_float(u);
+#else
+  memcpy(&s, &u, 4);
+#endif
+  return s;
+}
+
+#ifdef __CUDACC__
+// whole warps only (every thread of the warp calls it once, at the end of the kernel)
+template <int S>
+__device__ __forceinline__ void publish_amax(DynState* dyn, int net, int level, float amx) {
+  if constexpr (S == kFp16x3) {
+    if (dyn) {
+      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(amx));   // amx >= 0: uint order == float order
+      if ((threadIdx.x & 31) == 0 && m) atomicMax(&dyn->amax[net][level], m);
+    }
+  }
+}
+#endif
 
 // A K-major operand: `planes` stacked [plane][rows_alloc][kpad] matrices of elem
 struct Operand {

@@ -58,7 +58,7 @@ class Engine:
     """One engine per device.  See include/mamimo.h for the contract of every call."""
 
     def __init__(self, n_tx, n_rx, n_sc, n_ltf=None, n_ps=1, hidden=(1024, 1024), d_in=None, d_out=None,
-                 input_mode="ls", precision="tf32x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=6,
+                 input_mode="ls", precision="tf32x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=0,
                  mlp=True, kb_per_chunk=0, host_chunk_pkts=0, fc_single_cta=False, fc_sm_reserve=0):
         cfg = _capi.Config()
         lib.mamimo_config_init(C.byref(cfg))
@@ -212,20 +212,32 @@ class Engine:
         self.ls_estimate_raw(Y.ctypes.data, t, n_pkt, H.ctypes.data, t, _capi.MEM_HOST)
         return H
 
-    def estimate(self, Y, want_ls=False):
-        """Full path (mode C).  Returns (H_real, H_imag[, H_ls]); H_* float32 [n_pkt*n_rx*n_tx, d_out]."""
+    def poll_flags(self, stream=0):
+        """Wait for `stream` and raise MamimoError if a kernel of an earlier DEVICE-buffer call latched a range /
+        timeout / not-positive-definite condition (mamimo_poll_flags; device calls themselves only enqueue work)."""
+        check(lib.mamimo_poll_flags(self._h, C.c_void_p(stream) if stream else None), self._h)
+
+    def estimate(self, Y, want_ls=False, check_flags=True):
+        """Full path (mode C).  Returns (H_real, H_imag[, H_ls]); H_* float32 [n_pkt*n_rx*n_tx, d_out].
+        torch CUDA input: asynchronous on torch's current stream unless check_flags (default), which waits for the
+        stream and raises on a latched device error instead of handing back garbage."""
         n_pkt = self._y_info(Y)
         c = self.cfg
         rows = n_pkt * self.rows_per_pkt
         if _is_torch_cuda(Y):
             import torch
+            if Y.dtype not in (torch.complex64, torch.complex128):
+                raise TypeError("Y must be complex64 or complex128")
             Y = Y.contiguous()
             t = _capi.C128 if Y.dtype == torch.complex128 else _capi.C64
             Hr = torch.empty((rows, c.d_out), dtype=torch.float32, device=Y.device)
             Hi = torch.empty_like(Hr)
             Hls = torch.empty((n_pkt, c.n_rx, c.n_tx, c.n_sc), dtype=torch.complex64, device=Y.device) if want_ls else None
+            st = torch.cuda.current_stream(Y.device).cuda_stream
             self.estimate_raw(Y.data_ptr(), t, n_pkt, Hls.data_ptr() if want_ls else 0, Hr.data_ptr(), Hi.data_ptr(),
-                              _capi.MEM_DEVICE, torch.cuda.current_stream(Y.device).cuda_stream)
+                              _capi.MEM_DEVICE, st)
+            if check_flags:
+                self.poll_flags(st)
         else:
             Y = np.ascontiguousarray(Y)
             if Y.dtype not in (np.complex64, np.complex128):
@@ -238,11 +250,13 @@ class Engine:
                               Hi.ctypes.data, _capi.MEM_HOST)
         return (Hr, Hi, Hls) if want_ls else (Hr, Hi)
 
-    def predict_planes(self, X_real, X_imag):
+    def predict_planes(self, X_real, X_imag, check_flags=True):
         """Mode B: float32 [rows, d_in] x2 -> float32 [rows, d_out] x2 (inference.py:29-30)."""
         c = self.cfg
         if _is_torch_cuda(X_real):
             import torch
+            if not _is_torch_cuda(X_imag) or X_real.ndim != 2 or X_real.shape[1] != c.d_in or X_imag.shape != X_real.shape:
+                raise ValueError("planes must be two CUDA tensors [rows, d_in=%d]" % c.d_in)
             Xr, Xi = X_real.contiguous().float(), X_imag.contiguous().float()
             rows = int(Xr.shape[0])
             Yr = torch.empty((rows, c.d_out), dtype=torch.float32, device=Xr.device)
@@ -250,6 +264,8 @@ class Engine:
             check(lib.mamimo_predict_planes(self._h, C.c_void_p(Xr.data_ptr()), C.c_void_p(Xi.data_ptr()), rows,
                                             C.c_void_p(Yr.data_ptr()), C.c_void_p(Yi.data_ptr()), _capi.MEM_DEVICE,
                                             C.c_void_p(torch.cuda.current_stream(Xr.device).cuda_stream)), self._h)
+            if check_flags:
+                self.poll_flags(torch.cuda.current_stream(Xr.device).cuda_stream)
             return Yr, Yi
         Xr = np.ascontiguousarray(X_real, dtype=np.float32)
         Xi = np.ascontiguousarray(X_imag, dtype=np.float32)
@@ -321,7 +337,7 @@ class Engine:
         return (Hr, Hi, Hls) if want_ls else (Hr, Hi)
 
     # ------------------------------------------------------------------ LMMSE smoother
-    def lmmse(self, H_ls, tau_rms, snr_db):
+    def lmmse(self, H_ls, tau_rms, snr_db, check_flags=True):
         """LMMSE_ce over a batch (pg/LMMSE_ce.m:23-39 as called at pg/helperMIMOChannelEstimate.m:37-39).
         H_ls [n_pkt, n_rx, n_tx, n_sc] complex64/128 (numpy = host, torch CUDA = device); tau_rms scalar or [n_pkt];
         snr_db scalar, [n_rx] or [n_pkt, n_rx] (SNR(i) in dB).  Returns H_mmse, same shape / dtype / residence."""
@@ -342,6 +358,8 @@ class Engine:
             check(lib.mamimo_lmmse(self._h, C.c_void_p(H_ls.data_ptr()), t, n_pkt, dp(tau), dp(snr),
                                    C.c_void_p(out.data_ptr()), t, _capi.MEM_DEVICE,
                                    C.c_void_p(torch.cuda.current_stream(H_ls.device).cuda_stream)), self._h)
+            if check_flags:       # e.g. Rpp not positive definite in FP64
+                self.poll_flags(torch.cuda.current_stream(H_ls.device).cuda_stream)
             return out
         H_ls = np.ascontiguousarray(H_ls)
         if H_ls.dtype not in (np.complex64, np.complex128):

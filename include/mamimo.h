@@ -38,7 +38,7 @@ extern "C" {
 #define MAMIMO_API __attribute__((visibility("default")))
 #endif
 
-#define MAMIMO_ABI_VERSION 1
+#define MAMIMO_ABI_VERSION 2
 #define MAMIMO_MAX_HIDDEN 8
 
 typedef struct mamimo_engine mamimo_engine;
@@ -50,7 +50,7 @@ typedef enum {
   MAMIMO_ERR_NOMEM = 3,
   MAMIMO_ERR_STATE = 4,        /* e.g. estimate before weights are finalised */
   MAMIMO_ERR_UNSUPPORTED = 5,  /* e.g. no sm_100 device present */
-  MAMIMO_ERR_RANGE = 6,        /* split-fp16 operand overflow detected on device */
+  MAMIMO_ERR_RANGE = 6,        /* split-fp16 operand outside its range window (overflow or underflow), detected on device */
   MAMIMO_ERR_TIMEOUT = 7       /* a device-side pipeline wait timed out (kernel aborted itself) */
 } mamimo_status;
 
@@ -89,7 +89,10 @@ typedef struct {
   int32_t hidden[MAMIMO_MAX_HIDDEN];
   int32_t len_ltf;          /* mode A only: time-domain samples per (pkt,rx) fed to the net */
   int32_t max_pkts;         /* packets per internal chunk (workspace sizing); 0 = default */
-  int32_t act_scale_log2;   /* FP16X3 only: power-of-two operand scale (default 6) */
+  int32_t act_scale_log2;   /* FP16X3 only.  0 (default) = auto: every activation level gets a power-of-two scale chosen
+                               on the device per call from the measured input amax and weight-norm bounds, so the result
+                               does not depend on the amplitude of Y.  != 0 pins 2^act_scale_log2 for all levels (no
+                               amax pre-pass); overflow AND underflow of the fp16 window then raise MAMIMO_ERR_RANGE */
   int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (4) */
   int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default */
   int32_t fc_single_cta;    /* 1 = use the 1-CTA FC kernel instead of the CTA-pair (cta_group::2) kernel */
@@ -101,7 +104,8 @@ typedef struct {
   uint64_t kernel_launches;   /* engine kernels launched since create */
   uint64_t h2d_bytes;         /* bytes copied host->device by the engine */
   uint64_t d2h_bytes;
-  uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout, bit2 LMMSE matrix not positive definite */
+  uint32_t last_device_flags; /* bit0 range overflow, bit1 pipeline timeout, bit2 LMMSE matrix not positive definite,
+                                 bit3 range underflow (pinned act_scale_log2 only) */
   uint32_t graph_launches;    /* device-resident full-path calls issued as ONE CUDA-graph launch (captured once per
                                  (buffers, batch size, stream), replayed afterwards; MAMIMO_GRAPH=0 disables) */
 } mamimo_stats;
@@ -235,7 +239,12 @@ MAMIMO_API mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo
 /* tau_rms of LMMSE_ce.m:27-30 for h [n] (real, or complex interleaved when is_complex) */
 MAMIMO_API double mamimo_tau_rms(const double* h, int32_t n, int32_t is_complex);
 
+/* Error reporting of DEVICE-buffer calls.  Every entry point taking mem == MAMIMO_MEM_DEVICE only enqueues work on
+ * `stream` and returns; conditions its kernels detect (MAMIMO_ERR_RANGE, MAMIMO_ERR_TIMEOUT, LMMSE not-PD) are
+ * latched in a device flag word and reported -- and cleared -- by the next mamimo_synchronize (waits for the whole
+ * device) or mamimo_poll_flags (waits for `stream` only).  HOST-buffer calls are synchronous and report directly. */
 MAMIMO_API mamimo_status mamimo_synchronize(mamimo_engine* e);
+MAMIMO_API mamimo_status mamimo_poll_flags(mamimo_engine* e, void* stream);
 MAMIMO_API mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out);
 /* begin: bracket every engine kernel with a CUDA event pair on its stream; end: synchronise and sum them */
 MAMIMO_API mamimo_status mamimo_profile_begin(mamimo_engine* e);

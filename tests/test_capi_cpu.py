@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(mm.build.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), "missing export " + name
-    assert raw.mamimo_abi_version() == 1
+    assert raw.mamimo_abi_version() == capi.ABI_VERSION == 2
 
 
 def test_tables_bit_identical(golden_dir):
