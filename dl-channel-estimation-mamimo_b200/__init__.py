@@ -8,10 +8,10 @@ The directory name contains hyphens, so import it through the root-level shim:
     import mamimo_b200 as mm
     eng = mm.Engine(n_tx=32, n_rx=4, n_sc=1024, hidden=(1024, 1024))
 """
-from . import build, synth, sharding, pipeline  # noqa: F401
+from . import build, synth, sharding, pipeline, weights, cli  # noqa: F401
 from ._capi import MamimoError, PRECISIONS, INPUT_MODES  # noqa: F401
 from .engine import (Engine, CSIPredictor, helperMIMOChannelEstimate, vht_ltf256, carriers_locations,  # noqa: F401
                      default_p, pair_row, pinned_empty, tau_rms)
 
 __all__ = ["Engine", "CSIPredictor", "helperMIMOChannelEstimate", "vht_ltf256", "carriers_locations",
-           "default_p", "pair_row", "pinned_empty", "tau_rms", "MamimoError", "synth", "build", "sharding", "pipeline"]
+           "default_p", "pair_row", "pinned_empty", "tau_rms", "MamimoError", "synth", "build", "sharding", "pipeline", "weights", "cli"]

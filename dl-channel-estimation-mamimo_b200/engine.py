@@ -504,8 +504,9 @@ class CSIPredictor:
     """Drop-in for inference.py:6-68 backed by the CUDA engine (mode B).
 
     model_path holds 'real_weights.npz' / 'imag_weights.npz' (flat exports of the Keras layers:
-    W0,b0[,bn0_gamma,bn0_beta,bn0_mean,bn0_var],W1,...; TensorFlow/h5py are not needed) or is
-    given directly as nets={'real': layers, 'imag': layers}.
+    W0,b0[,bn0_gamma,bn0_beta,bn0_mean,bn0_var],W1,...; written by tools/keras_to_npz.py, TensorFlow/h5py are not
+    needed to load them), or the reference's own hdf5 / SavedModel artefacts when h5py / tensorflow are installed,
+    or the nets are given directly as nets={'real': layers, 'imag': layers}.
     """
 
     def __init__(self, model_path=None, experiment="RICE_RENEW", verbose=False, nets=None, precision="tf32x3",
@@ -528,18 +529,10 @@ class CSIPredictor:
                     print("  dense%d %s bn=%s" % (i, np.asarray(L["W"]).shape, L.get("bn") is not None))
 
     def load_model(self):
-        nets = {}
-        for name in ("real", "imag"):
-            z = np.load(os.path.join(self.path, name + "_weights.npz"))
-            layers, i = [], 0
-            while "W%d" % i in z:
-                L = {"W": z["W%d" % i], "b": z["b%d" % i], "bn": None}
-                if "bn%d_gamma" % i in z:
-                    L["bn"] = tuple(z["bn%d_%s" % (i, k)] for k in ("gamma", "beta", "mean", "var"))
-                layers.append(L)
-                i += 1
-            nets[name] = layers
-        return nets
+        """inference.py:14-22 loads <path>/{real,imag}_keras_model; here, in order: <d>_weights.npz (tools/keras_to_npz.py),
+        <d>_weights-improvement.hdf5 (needs h5py), <d>_keras_model (needs tensorflow) -- see weights.py."""
+        from . import weights
+        return weights.load_nets(self.path)
 
     def inference(self, input_batch):
         X = self.preprocess_data(input_batch)

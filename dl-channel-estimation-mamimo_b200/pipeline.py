@@ -68,9 +68,56 @@ def read_prediction_files(workdir, pkt_id, n_tx, n_rx):
     return csi, xs["real"], xs["imag"]
 
 
+def rebuild_rx_signal(x_real, x_imag, len_in, n_tx, n_rx):
+    """What pg/BER_test_maMIMO_LTF.m does with the `x` field of one packet's files: keep x(:,1:lenIn) (:203,206) and
+    take row (iRx-1)*nTXAnts+1 of each plane as the time-domain preamble of rx antenna iRx (:312-318).
+    Returns inputRXSig complex [len_in, n_rx] (MATLAB shape), the input of its ofdmdemod call (:324-326)."""
+    xr = np.asarray(x_real)[:, :len_in]
+    xi = np.asarray(x_imag)[:, :len_in]
+    sig = np.zeros((len_in, n_rx), dtype=np.complex128)
+    for irx in range(n_rx):
+        sig[:, irx] = xr[irx * n_tx, :] + 1j * xi[irx * n_tx, :]
+    return sig
+
+
+def run_test_mode_time(engine, rx_time, workdir, true_real=None, true_imag=None, first_pkt_id=1):
+    """`massiveMIMO_CSI_prediction_DNN.py --test` (:330-346,401-409) from the time-domain preamble the shipped
+    pipeline feeds its nets: rx_time complex [n_pkt, n_rx, lenLTF] (MATLAB inputRXSig [lenLTF x Nr] per packet,
+    pg/generate_maMIMO_LTF.m:326-327).  The engine is either
+      * a mode-A engine (input_mode='time_p': [LTF || P(:,iTx)] -> nets, the pipeline's own network), or
+      * a mode-C engine with the OFDM front-end configured (set_ofdm): demod -> LS -> nets (the north_star path).
+    Leaves test_csi_predictions_{real,imag}_<pkt>.mat with y = the prediction planes and x = the LTF part of the
+    net input (:80,405) -- row (pkt, rx, tx) holds the real / imag plane of rx's time-domain preamble, which is what
+    pg/BER_test_maMIMO_LTF.m:203,206,312-318 turns back into inputRXSig.  Returns (H_real, H_imag)."""
+    rx_time = np.asarray(rx_time)
+    c = engine.cfg
+    if rx_time.ndim != 3 or rx_time.shape[1] != c.n_rx or not np.iscomplexobj(rx_time):
+        raise ValueError("rx_time must be complex [n_pkt, n_rx=%d, lenLTF]" % c.n_rx)
+    if engine.input_mode == "time_p":
+        Hr, Hi = engine.predict_time(rx_time.real, rx_time.imag)
+    elif engine.input_mode == "ls":
+        Hr, Hi = engine.estimate_time(rx_time.astype(np.complex64, copy=False) if rx_time.dtype != np.complex128 else rx_time)
+    else:
+        raise ValueError("run_test_mode_time needs a mode-A ('time_p') or mode-C ('ls' + set_ofdm) engine")
+    # every pair row of (pkt, rx) carries the same LTF (the reference stores it once per rx under a hash,
+    # create_massiveMIMO_CSIest_dnn_dataset.py:50-59, and the generator replicates it per tx, :307-309)
+    rows = c.n_tx * c.n_rx
+    Hr, Hi = np.asarray(Hr), np.asarray(Hi)
+    for p in range(rx_time.shape[0]):               # one packet at a time: x is n_tx copies of each rx row (10 MB/plane at 32x4x10240)
+        sl = slice(p * rows, (p + 1) * rows)
+        x_r = np.repeat(rx_time[p].real.astype(np.float64), c.n_tx, axis=0)
+        x_i = np.repeat(rx_time[p].imag.astype(np.float64), c.n_tx, axis=0)
+        write_prediction_files(workdir, Hr[sl], Hi[sl], c.n_tx, c.n_rx, x_r, x_i,
+                               None if true_real is None else np.asarray(true_real)[sl],
+                               None if true_imag is None else np.asarray(true_imag)[sl], first_pkt_id + p)
+    return Hr, Hi
+
+
 def run_test_mode(engine, Y, workdir, true_real=None, true_imag=None, first_pkt_id=1, keep_input=True):
-    """Mode-C equivalent of `massiveMIMO_CSI_prediction_DNN.py --test`: estimate a batch of packets on the
-    GPU and leave one pair of .mat files per packet in workdir.  Returns (H_real, H_imag, H_ls)."""
+    """Frequency-domain (mode C) variant: estimate a batch of already-demodulated packets Y on the GPU and leave one
+    pair of .mat files per packet in workdir.  Its `x` field holds the nets' input here, i.e. the H_LS planes -- NOT
+    the time-domain preamble BER_test_maMIMO_LTF.m:312-318 rebuilds its rx signal from; use run_test_mode_time when
+    the files feed that evaluator.  Returns (H_real, H_imag, H_ls)."""
     Hr, Hi, Hls = engine.estimate(Y, want_ls=True)
     c = engine.cfg
     x_r = x_i = None

@@ -280,7 +280,58 @@ def run_matlab_hot_path():
     return out
 
 
+# ---------------------------------------------------------------- 6. BER_test_maMIMO_LTF.m reader of the prediction files
+def ber_test_reader_source(ref=REF):
+    """The literal lines of pg/BER_test_maMIMO_LTF.m that consume one packet's pair of prediction files -- the
+    isSeparateFiles branch (:198-221: file names, load, .y / .x(:,1:lenIn), CSI rebuild loop), `CSI_dnn = complex(...)`
+    (:226) and the rebuild of the time-domain rx signal from the x planes (:312-318) -- wrapped in a function header so
+    mini_matlab can run them.  Nothing but the header / trailer is written here."""
+    ber = open(os.path.join(ref, "packet_generation/phased_arr/BER_test_maMIMO_LTF.m"), encoding="latin-1").read()
+    lines = ber.splitlines()
+    a0 = next(i for i, l in enumerate(lines) if l.strip().startswith("real_file_pkt = insertBefore("))
+    a1 = next(i for i in range(a0, len(lines)) if lines[i].strip() == "end" and lines[i + 1].strip() == "end"
+              and "CSI_dnn_imag(:,iTX,iRX)" in lines[i - 1]) + 1            # closes `for iTX`, then `for iRX`
+    part_a = lines[a0:a1 + 1]
+    assert "load(real_file_pkt);" in "".join(part_a) and "inputLTF_IMAG = inputLTF_IMAG(:,1:lenIn);" in "\n".join(part_a)
+    b0 = next(i for i, l in enumerate(lines) if l.strip().startswith("CSI_dnn = complex(CSI_dnn_real,CSI_dnn_imag)"))
+    c0 = next(i for i, l in enumerate(lines) if l.strip().startswith("inputRXSig_real = zeros(lenIn,nRXAnts);"))
+    c1 = next(i for i in range(c0, len(lines)) if lines[i].strip().startswith("inputRXSig = complex(inputRXSig_real,inputRXSig_imag);"))
+    body = "\n".join(part_a + [lines[b0]] + lines[c0:c1 + 1])
+    return ("function [CSI_dnn, inputRXSig] = ber_reader(real_csi_pred, imag_csi_pred, p, lenIn, nSubCar, nTXAnts, nRXAnts)\n"
+            "CSI_dnn_real = zeros(nSubCar,nTXAnts,nRXAnts);\nCSI_dnn_imag = zeros(nSubCar,nTXAnts,nRXAnts);\n"   # :182-183
+            + body + "\nend\n")
+
+
+def run_ber_test_reader():
+    """Files written by this repo's writer (pipeline.write_prediction_files, no GPU involved), read back by the
+    reference's own lines.  Stores the planes that went in and what MATLAB's side makes of them."""
+    import tempfile
+    from mini_matlab import MatlabFile
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import mamimo_b200 as mm
+    n_tx, n_rx, n_sc, len_in, n_pkt = 4, 3, 10, 24, 2
+    rng = np.random.default_rng(6705)
+    rows = n_tx * n_rx
+    y_r = rng.standard_normal((n_pkt * rows, n_sc)).astype(np.float32)
+    y_i = rng.standard_normal((n_pkt * rows, n_sc)).astype(np.float32)
+    sig = rng.standard_normal((n_pkt, n_rx, len_in)) + 1j * rng.standard_normal((n_pkt, n_rx, len_in))
+    x_r = np.repeat(sig.real, n_tx, axis=1).reshape(-1, len_in)
+    x_i = np.repeat(sig.imag, n_tx, axis=1).reshape(-1, len_in)
+    m = MatlabFile(ber_test_reader_source())
+    out = dict(n_tx=n_tx, n_rx=n_rx, len_in=len_in, y_real=y_r, y_imag=y_i, x_real=x_r, x_imag=x_i)
+    with tempfile.TemporaryDirectory() as td:
+        mm.pipeline.write_prediction_files(td, y_r, y_i, n_tx, n_rx, x_r, x_i, first_pkt_id=1)
+        for p in range(1, n_pkt + 1):
+            csi, rx = m.call("ber_reader", [os.path.join(td, "test_csi_predictions_real.mat"),
+                                            os.path.join(td, "test_csi_predictions_imag.mat"),
+                                            float(p), float(len_in), float(n_sc), float(n_tx), float(n_rx)], 2)
+            out["csi_dnn_%d" % p] = csi
+            out["input_rx_sig_%d" % p] = rx
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "ref_ber_test_reader.npz"), **run_ber_test_reader())
     np.savez_compressed(os.path.join(HERE, "ref_matlab_ls_lmmse.npz"), **run_matlab_hot_path())
     install_stub_tf(lambda path: None)
     np.savez_compressed(os.path.join(HERE, "ref_data_generator_reshape.npz"), **run_data_generator_reshape())

@@ -115,6 +115,12 @@ def tokenize(src):
                 space = False
                 pos = end + 1
                 continue
+        if text[pos] == '"':                      # string-array literal "..." (treated like a char vector here)
+            end = text.index('"', pos + 1)
+            toks.append(Tok("str", text[pos + 1:end], space))
+            space = False
+            pos = end + 1
+            continue
         m = _TOKEN.match(text, pos)
         if not m:
             raise MatlabError("cannot tokenize at %r" % text[pos:pos + 30])
@@ -556,6 +562,15 @@ class MatlabFile:
             return [np.mod(A[0], A[1])]
         if name == "isempty":
             return [mat(float(A[0].size == 0))]
+        if name in ("num2str", "int2str"):
+            v = A[0] if isinstance(A[0], str) else np.asarray(A[0]).real.item()
+            return [v if isinstance(v, str) else (str(int(round(v))) if float(v).is_integer() or name == "int2str" else "%.4g" % v)]
+        if name == "strcat":
+            return ["".join(a if isinstance(a, str) else str(a) for a in A)]
+        if name == "insertBefore":              # insertBefore(str, pat, new): before every occurrence of pat
+            return [A[0].replace(A[1], A[2] + A[1])]
+        if name == "disp":
+            return [np.zeros((0, 0))]
         if name == "pi":
             return [mat(np.pi)]
         if name in ("eps",):
@@ -599,7 +614,11 @@ class MatlabFile:
                     if nm != "~":
                         env[nm] = v
             elif kind == "expr":
-                self._eval(s[1], env)
+                if s[1][0] == "call" and s[1][1] == ("id", "load") and "load" not in env:
+                    # load(file): every variable of the MAT-file lands in the workspace (structs keep their fields)
+                    self._load_into(env, self._eval(s[1][2][0], env))
+                else:
+                    self._eval(s[1], env)
             elif kind == "for":
                 rng = self._eval(s[2], env)
                 cols = rng.reshape(rng.shape[0], -1, order="F")
@@ -615,6 +634,19 @@ class MatlabFile:
                         break
                 if not done and s[2] is not None:
                     self._exec_block(s[2], env)
+
+    @staticmethod
+    def _load_into(env, path):
+        from scipy.io import loadmat
+        for k, v in loadmat(path, struct_as_record=False, squeeze_me=False).items():
+            if k.startswith("__"):
+                continue
+            if isinstance(v, np.ndarray) and v.dtype == object and v.size == 1 and hasattr(v.flat[0], "_fieldnames"):
+                st = v.flat[0]
+                env[k] = _Struct({f: mat(np.asarray(getattr(st, f), dtype=np.complex128 if np.iscomplexobj(getattr(st, f)) else np.float64))
+                                  for f in st._fieldnames})
+            else:
+                env[k] = mat(np.asarray(v, dtype=np.complex128 if np.iscomplexobj(v) else np.float64))
 
     @staticmethod
     def _truth(v):

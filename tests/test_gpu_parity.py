@@ -511,6 +511,92 @@ def test_test_mode_driver_writes_reference_file_contract(tmp_path):
         assert np.array_equal(x_r, Hls[p].reshape(-1, nsc).real)
 
 
+def test_test_mode_time_driver_files_feed_the_matlab_evaluator(tmp_path):
+    """run_test_mode_time (massiveMIMO_CSI_prediction_DNN.py:330-346,401-409 from the time-domain preamble): the files
+    hold y = prediction planes and x = the LTF part of the net input, from which pg/BER_test_maMIMO_LTF.m:203,206,
+    312-318 rebuilds inputRXSig (reader mirror pinned on the reference's lines: tests/test_file_contract.py).
+    Both engines that accept the time-domain preamble: mode A (the pipeline's network) and mode C behind ofdmdemod."""
+    from oracle import ofdm
+    nt, nr, npkt = 8, 2, 3
+    car = tables.carriers_locations()
+    xp = tables.ltf_at_carriers().astype(np.float64)
+    Yf, _ = mm.synth.make_packets(51, npkt, nt, nr, 234, snr_db=10.0, x_tones=xp, dtype=np.complex128)
+    sig = ofdm.ofdm_mod(Yf, 256, 64, car) * 256                             # [npkt, nr, nt*320] complex128
+    len_ltf = sig.shape[2]
+    P = tables.sylvester_hadamard(nt)
+    # mode A: [LTF || P row] -> 64 -> 234
+    netsA = mm.synth.make_nets(len_ltf + nt, (64,), 234)
+    dA = tmp_path / "a"
+    dA.mkdir()
+    with mm.Engine(nt, nr, 8, hidden=(64,), d_in=len_ltf + nt, d_out=234, input_mode="time_p", len_ltf=len_ltf,
+                   precision="tf32x3") as eng:
+        eng.set_pilots(None, P)
+        eng.load_weights(netsA)
+        Hr, Hi = mm.pipeline.run_test_mode_time(eng, sig, str(dA), first_pkt_id=1)
+    allrows = np.arange(npkt * nr * nt)
+    refA = {}
+    for part, name in ((np.real, "real"), (np.imag, "imag")):
+        xsig, xpp = postproc.assemble_mode_a(part(sig).astype(np.float32), P.T, allrows, nr, nt)
+        refA[name] = mlp.forward(np.concatenate([xsig, xpp], axis=1), netsA[name])
+    # mode C: ofdmdemod -> LS -> 128 -> 234
+    netsC = mm.synth.make_nets(234, (128,), 234)
+    dC = tmp_path / "c"
+    dC.mkdir()
+    with mm.Engine(nt, nr, 234, hidden=(128,), precision="tf32x3") as eng:
+        eng.set_pilots(xp, None)
+        eng.load_weights(netsC)
+        eng.set_ofdm(256, 64, 64, car)
+        mm.pipeline.run_test_mode_time(eng, sig.astype(np.complex64), str(dC), first_pkt_id=1)
+    Yref = ofdm.ofdm_demod(sig.astype(np.complex64), 256, 64, 64, car)
+    _, rC_r, rC_i = oracle_full(Yref, P, xp, 1, netsC)
+    for p in range(npkt):
+        sl = slice(p * nt * nr, (p + 1) * nt * nr)
+        for wd, ref_r, ref_i, sig_in in ((dA, refA["real"], refA["imag"], sig), (dC, rC_r, rC_i, sig.astype(np.complex64))):
+            csi, x_r, x_i = mm.pipeline.read_prediction_files(str(wd), p + 1, nt, nr)
+            assert rel_l2(postproc.rows_to_csi(ref_r[sl] + 1j * ref_i[sl], nt, nr), csi) <= TOL_DNN
+            rx = mm.pipeline.rebuild_rx_signal(x_r, x_i, len_ltf, nt, nr)    # BER_test_maMIMO_LTF.m:312-318
+            assert np.array_equal(rx, sig_in[p].T.astype(np.complex128))
+
+
+def test_cli_test_branch_on_the_gpu(tmp_path):
+    """The argv-compatible --test entry (full_pipeline_maMIMO_DNNEst.sh:47) with the real engine, fp16x3 and tf32x3."""
+    import pickle
+    from scipy.io import loadmat
+    n_pkt, nt, nr, len_ltf, nsc, hidden = 6, 8, 2, 320, 52, (64, 48)
+    rng = np.random.default_rng(52)
+    ltf = (rng.standard_normal((n_pkt, nr, len_ltf)) + 1j * rng.standard_normal((n_pkt, nr, len_ltf))) * 0.06
+    y = rng.standard_normal((n_pkt * nr * nt, nsc)) + 1j * rng.standard_normal((n_pkt * nr * nt, nsc))
+    X = np.zeros((n_pkt * nr * nt, 2), dtype=np.int64)
+    LTF = {}
+    for p in range(n_pkt):
+        for irx in range(nr):
+            h = 7000 + p * nr + irx
+            LTF[h] = {"real": ltf[p, irx].real.copy(), "imag": ltf[p, irx].imag.copy()}
+            X[p * nr * nt + irx * nt:p * nr * nt + (irx + 1) * nt] = np.stack([np.full(nt, h), np.arange(nt)], axis=1)
+    Ppk = tables.sylvester_hadamard(nt).T.copy()
+    ds = {"X": X, "y": {"real": y.real.copy(), "imag": y.imag.copy()}, "LTF": LTF, "P": Ppk,
+          "simParams": {"FFTLength": 32.0, "CPLen": 8.0, "numSym": 8.0, "symOffset": 8.0, "nTX": nt, "nRX": nr}}
+    pk = str(tmp_path / "testDataset.b")
+    with open(pk, "wb") as f:
+        pickle.dump(ds, f)
+    nets = mm.synth.make_nets(len_ltf + nt, hidden, nsc)
+    for d in ("real", "imag"):
+        mm.weights.save_npz(str(tmp_path / (d + "_weights.npz")), nets[d])
+    allrows = np.arange(n_pkt * nr * nt)
+    for prec in ("tf32x3", "fp16x3"):
+        wd = tmp_path / ("out_" + prec)
+        wd.mkdir()
+        rc = mm.cli.main(["--test", "-x", pk, "--nn", "64", "48", "-d", str(wd), "--modeldir", str(tmp_path), "--useGPU", "0",
+                          "--useBN", "--datasource", "matlab_maMimo", "--valSameTrain", "--precision", prec, "--chunk-pkts", "4"])
+        assert rc == 0
+        for d, part in (("real", np.real), ("imag", np.imag)):
+            xsig, xpp = postproc.assemble_mode_a(part(ltf).astype(np.float32), Ppk, allrows, nr, nt)
+            ref = mlp.forward(np.concatenate([xsig, xpp], axis=1), nets[d])
+            got = np.concatenate([loadmat(str(wd / ("test_csi_predictions_%s_%d.mat" % (d, p + 1))), struct_as_record=False,
+                                          squeeze_me=True)["all_pkts_csi_nn_out"].y for p in range(n_pkt)])
+            assert rel_l2(ref, got) <= TOL_DNN, (prec, d)
+
+
 def test_staged_estimate_matches_full_call():
     """mamimo_estimate_stages(LS|real) then (imag) == mamimo_estimate, bitwise (used to overlap the all-gather)."""
     import torch
