@@ -24,6 +24,33 @@ NVCC_FLAGS = [
 ]
 
 
+# The MEX gateway executed without MATLAB: mex_gateway.cpp + the functional mini runtime (csrc/mex_runtime) + a C
+# driver for the tests, linked against the product library.  Test infrastructure; built here so it travels with it.
+MEX_HARNESS_PATH = os.path.join(PKG_DIR, "libmamimo_mex_harness.so")
+MEX_SOURCES = ["mex_gateway.cpp", os.path.join("mex_runtime", "mex_runtime.cpp"), os.path.join("mex_runtime", "mex_harness.cpp")]
+MEX_HEADERS = [os.path.join("mex_runtime", "mex.h"), os.path.join("mex_runtime", "mex_runtime.hpp"),
+               os.path.join("..", "..", "include", "mamimo.h")]
+
+
+def build_mex_harness(force=False):
+    """g++ -shared: the gateway's mexFunction behind a ctypes-callable driver.  Returns the .so path."""
+    deps = [os.path.join(CSRC, s) for s in MEX_SOURCES + MEX_HEADERS] + [LIB_PATH]
+    if not force and os.path.exists(MEX_HARNESS_PATH) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(MEX_HARNESS_PATH) for d in deps if os.path.exists(d)):
+        return MEX_HARNESS_PATH
+    gxx = shutil.which("g++")
+    if not gxx:
+        raise RuntimeError("g++ not found: cannot build the MEX harness")
+    cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-shared", "-fPIC", "-fvisibility=hidden",
+           "-I" + os.path.join(CSRC, "mex_runtime"), "-I" + os.path.join(PKG_DIR, "..", "include"),
+           "-o", MEX_HARNESS_PATH] + [os.path.join(CSRC, s) for s in MEX_SOURCES] + \
+          ["-L" + PKG_DIR, "-lmamimo_b200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ (MEX harness) failed:\n" + res.stdout + res.stderr)
+    return MEX_HARNESS_PATH
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -56,3 +83,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_mex_harness(force="--force" in sys.argv))

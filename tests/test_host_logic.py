@@ -41,15 +41,19 @@ def test_prediction_files_missing_dir_exits_zero(tmp_path):
     assert ei.value.code == 0
 
 
-def test_mex_gateway_compiles_against_stub():
+def test_mex_gateway_builds_warning_free_and_stays_thin():
+    """The gateway is compiled for real into the harness the MEX tests execute (tests/test_mex_gateway.py); here:
+    no warnings under -Wall -Wextra against the mini runtime's mex.h, and it stays a thin shim over the C ABI."""
     gxx = shutil.which("g++")
     if not gxx:
         pytest.skip("no g++")
     src = os.path.join(PKG, "csrc", "mex_gateway.cpp")
-    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(PKG, "csrc", "mex_stub"),
-                          "-I" + os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                          "-I" + os.path.join(PKG, "csrc", "mex_runtime"), "-I" + os.path.join(ROOT, "include"), src],
+                         capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    assert len(open(src).read().splitlines()) < 200          # stays a thin shim over the C ABI
+    assert len(open(src).read().splitlines()) < 200
+    assert os.path.exists(mm.build.build_mex_harness())
 
 
 def test_helper_argument_validation_without_gpu():
