@@ -25,8 +25,29 @@ sys.path.insert(0, ROOT)
 
 NT, NR, NSC, HIDDEN, SNR_DB = 32, 4, 1024, (1024, 1024), 10.0
 WORKLOAD = "configs[1]: Nt=32 Nr=4, 1024 sc, 500-packet batch, SNR=10 dB, FC 1024-1024-1024-1024 x2 nets"
+METRIC = "channel-estimates/sec (32x4, 1024-sc pkts)"
 MLP_FLOP_PER_PKT = NT * NR * 2 * 2 * (NSC * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * NSC)
 LS_BYTES_PER_PKT = NR * NT * NSC * 8 * 2                                                            # Y in + H planes out
+SNR_LEVELS = None          # c3: per-packet SNR levels cycled through the batch
+
+# BASELINE.json configs.  c2 = configs[1] is the bench line (the config the metric is quoted on); the others are the
+# larger parity configs, timed with the same code so the driver can run them too.
+CONFIGS = {
+    "c2": dict(nt=32, nr=4, nsc=1024, npkt=500, e2e_pkts=None,
+               workload="configs[1]: Nt=32 Nr=4, 1024 sc, 500-packet batch, SNR=10 dB, FC 1024-1024-1024-1024 x2 nets",
+               metric="channel-estimates/sec (32x4, 1024-sc pkts)"),
+    "c3": dict(nt=32, nr=4, nsc=1024, npkt=3000, e2e_pkts=1000, snr_levels=[-25, -20, -15, -10, -5, 0, 5, 10],
+               workload="configs[2]: Nt=32 Nr=4, 1024 sc, 3000-packet batch, SNR sweep -25..10 dB (8 levels interleaved), "
+                        "FC 1024-1024-1024-1024 x2 nets",
+               metric="channel-estimates/sec (32x4, 1024-sc pkts)"),
+    "c4": dict(nt=64, nr=8, nsc=2048, npkt=3000, e2e_pkts=250,
+               workload="configs[3]: Nt=64 Nr=8, 2048 sc, 3000-packet batch, SNR=10 dB, FC 2048-1024-1024-2048 x2 nets",
+               metric="channel-estimates/sec (64x8, 2048-sc pkts)"),
+    "c5": dict(nt=64, nr=8, nsc=2048, npkt=125, e2e_pkts=None,
+               workload="configs[4]: Nt=64 Nr=8, 2048 sc, 3000 packets per GPU as chunks of 125 per step, FC 2048-1024-1024-2048 "
+                        "x2 nets, all-gather of H-hat per chunk",
+               metric="channel-estimates/sec (64x8, 2048-sc pkts)"),
+}
 
 
 def measured_peaks():
@@ -96,7 +117,8 @@ def cpu_reference_run(n_pkt_sample, steps, warmup):
     x = synth.make_pilots(NSC)
     nets = synth.make_nets(NSC, HIDDEN, NSC)
     P = synth.sylvester(NT)
-    Y, _ = synth.make_packets(1, n_pkt_sample, NT, NR, NSC, SNR_DB, x_tones=x)
+    snr = SNR_DB if SNR_LEVELS is None else np.resize(np.asarray(SNR_LEVELS, dtype=np.float64), n_pkt_sample)
+    Y, _ = synth.make_packets(1, n_pkt_sample, NT, NR, NSC, snr, x_tones=x)
     Yt = torch.from_numpy(Y)
     tnets = {}
     for name in ("real", "imag"):
@@ -139,10 +161,11 @@ def run_reference_arm(args):
     n_sample = args.cpu_sample
     val, dt, cores = cpu_reference_run(n_sample, max(1, args.steps), max(0, args.warmup))
     line = {
-        "impl": "reference", "metric": "channel-estimates/sec (32x4, 1024-sc pkts)", "value": val, "unit": "packets/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "packets/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 LS + f32 FC (CPU)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_pkts_per_step": n_sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD},
+        "sample_pkts_per_step": n_sample,
         "cpu_baseline": {"value": val, "unit": "packets/s", "cores": cores, "kind": "port",
                          "sample": "%d packets per step (torch-CPU c128 LS + fp32 FC, batch=Nt*Nr per predict)" % n_sample},
         "e2e": {"value": val, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,6 +203,50 @@ def bind_to_gpu_numa_node(index):
 
 
 # --------------------------------------------------------------------------- our arm
+def copy_ceiling_probe(torch, dev, world, dist, mib=256, reps=4):
+    """Pinned-copy ceiling of this box measured in the run: plain cudaMemcpyAsync H2D alone, D2H alone and both at once
+    (the e2e path is duplex), per rank and summed over ranks running at the same time.  GB/s."""
+    n = mib << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(h2d, d2h):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return reps * n / (time.perf_counter() - t0) / 1e9
+
+    timed(True, True)
+    res = {"h2d_alone": timed(True, False), "d2h_alone": timed(False, True), "duplex_each_way": timed(True, True)}
+    if world > 1:
+        t = torch.tensor([res["h2d_alone"], res["d2h_alone"], res["duplex_each_way"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        res.update({"aggregate_h2d_alone": float(t[0]), "aggregate_d2h_alone": float(t[1]), "aggregate_duplex_each_way": float(t[2])})
+    return res
+
+
+def traffic_from_profiles(kernel):
+    """DRAM bytes per launch of `kernel` from the ncu --set full capture committed under profiles/ (a run under ncu is
+    never a bench run, so this cannot be measured live); returns (bytes | None, source)."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tp):
+        return None, None
+    d = json.load(open(tp)).get(kernel, {})
+    return d.get("bytes_per_launch"), d.get("source")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -197,22 +264,24 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     npkt = args.npkt
+    cfg_id = 1
     x = mm.synth.make_pilots(NSC)
     nets = mm.synth.make_nets(NSC, HIDDEN, NSC)
-    # per-rank packet shard: rank r owns global packets [r*npkt, (r+1)*npkt)  (weak scaling)
+    # per-rank packet shard: rank r owns global packets [r*npkt, (r+1)*npkt)  (weak scaling); gen_pkts distinct synthetic
+    # packets are generated on the host and tiled ON THE DEVICE to npkt (c4: 23 GiB of Y never exists on the host)
     gen_pkts = min(npkt, args.gen_pkts)
-    Yg, _ = mm.synth.make_packets(1, gen_pkts, NT, NR, NSC, SNR_DB, x_tones=x, first_pkt=rank * npkt)
+    snr = SNR_DB if SNR_LEVELS is None else np.resize(np.asarray(SNR_LEVELS, dtype=np.float64), gen_pkts)
+    Yg, _ = mm.synth.make_packets(cfg_id, gen_pkts, NT, NR, NSC, snr, x_tones=x, first_pkt=rank * npkt)
     reps = (npkt + gen_pkts - 1) // gen_pkts
-    Yh = torch.from_numpy(np.concatenate([Yg] * reps)[:npkt].copy())
-    if not args.no_e2e:
-        Yh = Yh.pin_memory()
-    Yd = Yh.to(dev)
+    Yd = torch.from_numpy(Yg).to(dev).repeat(reps, 1, 1, 1)[:npkt].contiguous()
     rows = npkt * NT * NR
     Hr = torch.empty((rows, NSC), dtype=torch.float32, device=dev)
     Hi = torch.empty_like(Hr)
-    host_rows = 64 if args.no_e2e else rows
-    Hr_h = torch.empty((host_rows, NSC), dtype=torch.float32).pin_memory()
-    Hi_h = torch.empty((host_rows, NSC), dtype=torch.float32).pin_memory()
+    e2e_n = 0 if args.no_e2e else min(npkt, args.e2e_pkts or npkt)
+    e2e_rows = max(64, e2e_n * NT * NR)
+    Yh = torch.from_numpy(np.concatenate([Yg] * ((max(e2e_n, 1) + gen_pkts - 1) // gen_pkts))[:max(e2e_n, 1)].copy()).pin_memory()
+    Hr_h = torch.empty((e2e_rows, NSC), dtype=torch.float32).pin_memory()
+    Hi_h = torch.empty((e2e_rows, NSC), dtype=torch.float32).pin_memory()
     gathered = None
     if world > 1:
         gathered = [torch.empty((world * rows, NSC), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -270,11 +339,12 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
+    eng.poll_flags(stream.cuda_stream)           # a latched range / timeout condition must fail the run, not time garbage
 
-    # ---- timed region 1: device-resident (value).  At N = 1 each step is ONE CUDA-graph launch (7 kernels).
+    # ---- timed region 1: device-resident (value)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = eng.stats()["kernel_launches"]
+    st0 = eng.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -284,17 +354,20 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()                      # clocks / throttle reasons DURING the value region only
-    launches = eng.stats()["kernel_launches"] - l0
+    st1 = eng.stats()
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    graph_launches = st1["graph_launches"] - st0["graph_launches"]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * npkt / (ms_step * 1e-3)
+    eng.poll_flags(stream.cuda_stream)
 
     # ---- the same K steps again with every kernel bracketed by CUDA events on its stream (live per-kernel-class
-    # profile for the rooflines; plain launches, because events inside a replayed graph cannot be read back).
-    # One second of idle first: the board is power-capped under sustained tensor load (sw_power_cap), and the second
-    # of two back-to-back regions would be measured at lower clocks than the first.
+    # profile for the rooflines; plain launches on ONE stream, because events inside a replayed graph cannot be read
+    # back and brackets on two interleaved streams would overlap).  One second of idle first: back to back, the second
+    # region would be measured deeper into the board's power-capped regime than the first.
     time.sleep(1.0)
     for _ in range(3):
         step_device()
@@ -321,22 +394,44 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         value_compute_only = world * npkt / (float(t.item()) / args.steps * 1e-3)
 
-    # fused gather self-check: the planes written by the kernels of all ranks == an NCCL all-gather of the same data
-    gather_check = None
-    if fused:
+    # ---- checks outside the timed regions
+    # (1) fused gather: the planes written by the kernels of all ranks == an NCCL all-gather of the same data, bitwise
+    # (2) parity: one gathered packet PER RANK against the FP64 oracle on rank 0 (N = 1: one packet of the batch)
+    gather_check, parity = None, None
+    if world > 1:
         eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
         dist.all_gather_into_tensor(gathered[0], Hr)
         dist.all_gather_into_tensor(gathered[1], Hi)
         barrier()
-        ok = torch.tensor([int(torch.equal(gathered[0], g_real) and torch.equal(gathered[1], g_imag))], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        gather_check = bool(ok.item())
+        if fused:
+            ok = torch.tensor([int(torch.equal(gathered[0], g_real) and torch.equal(gathered[1], g_imag))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            gather_check = bool(ok.item())
+    if rank == 0 and not args.no_parity_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import tables as o_tables, postproc as o_post
+        from _util import oracle_full
+        planes = (g_real, g_imag) if fused else ((gathered[0], gathered[1]) if world > 1 else (Hr, Hi))
+        if world == 1:
+            eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+            torch.cuda.synchronize(dev)
+        errs = []
+        rpp = NT * NR
+        for r in range(world):
+            snr_r = SNR_DB if SNR_LEVELS is None else float(SNR_LEVELS[0])
+            Yr_, _ = mm.synth.make_packets(cfg_id, 1, NT, NR, NSC, snr_r, x_tones=x, first_pkt=r * npkt)
+            _, ref_r, ref_i = oracle_full(Yr_, o_tables.sylvester_hadamard(NT), x, 1, nets)
+            got_r = planes[0][r * rows:r * rows + rpp].cpu().numpy()
+            got_i = planes[1][r * rows:r * rows + rpp].cpu().numpy()
+            errs.append(float(o_post.rel_l2(ref_r + 1j * ref_i, got_r.astype(np.float64) + 1j * got_i)))
+        parity = {"rel_l2_vs_oracle_per_rank": errs, "max": max(errs), "bound": 1e-5, "ok": bool(max(errs) <= 1e-5),
+                  "what": "first packet of every rank's shard, read from rank 0's %s planes" % ("gathered" if world > 1 else "output")}
 
     # ---- timed region 2: end to end through the C ABI with pinned HOST buffers
     def step_host():
-        eng.estimate_raw(Yh.data_ptr(), 0, npkt, 0, Hr_h.data_ptr(), Hi_h.data_ptr(), 0)
+        eng.estimate_raw(Yh.data_ptr(), 0, e2e_n, 0, Hr_h.data_ptr(), Hi_h.data_ptr(), 0)
 
-    e2e_steps = 0 if args.no_e2e else args.steps
+    e2e_steps = 0 if e2e_n == 0 else args.steps
     for _ in range(2 if e2e_steps else 0):
         step_host()
     barrier()
@@ -348,33 +443,38 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * npkt / float(t.item())
-    checksum = float(Hr_h[:: max(1, host_rows // 64)].double().sum().item()) if e2e_steps else None    # device->host result actually read
+    e2e_val = world * e2e_n / float(t.item()) if e2e_steps else None
+    checksum = float(Hr_h[:: max(1, e2e_rows // 64)].double().sum().item()) if e2e_steps else None    # device->host result actually read
+    ceiling = copy_ceiling_probe(torch, dev, world, dist) if e2e_steps else None
 
     # ---- roofline of the dominant kernel (FC layers on the tensor pipe), from the live profile
     peaks, peak_src = measured_peaks()
     fc_ms_per_step = prof["fc_ms"] / args.steps
     ls_ms_per_step = prof["ls_ms"] / args.steps
     fc_tflops = MLP_FLOP_PER_PKT * npkt / (fc_ms_per_step * 1e-3) / 1e12 if fc_ms_per_step > 0 else 0.0
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
     fc_name = "fc_tc2_kernel" if args.precision != "fp32_simt" else "fc_simt_kernel"
+    is_bench_shape = args.precision == "fp16x3" and args.config == "c2" and npkt == 500
+    fc_traffic, fc_src = traffic_from_profiles(fc_name) if is_bench_shape else (None, None)
+    ls_traffic, ls_src = traffic_from_profiles("ls_kernel") if is_bench_shape else (None, None)
     roofline = {"bound": "tensor", "kernel": fc_name,
                 "achieved": fc_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": fc_tflops / peaks["bf16_tflops"], "peak_source": peak_src + " bf16 burst (cuBLAS)",
-                "traffic": (traffic.get(fc_name, {}).get("bytes_per_launch") if args.precision == "fp16x3" and npkt == 500 else None),
-                "traffic_unit": "bytes/launch (ncu dram read+write)", "flop_per_launch": MLP_FLOP_PER_PKT * npkt / 6,
+                "traffic": fc_traffic, "traffic_source": fc_src,
+                "traffic_unit": "bytes/launch (ncu dram read+write, committed capture)",
+                "flop_per_launch": MLP_FLOP_PER_PKT * npkt / max(1, prof["fc_launches"] // args.steps),
                 "avg_launch_ms": prof["fc_ms"] / max(1, prof["fc_launches"]),
                 "share_of_step": fc_ms_per_step / ms_prof_step if ms_prof_step > 0 else None,
-                "mma_passes": {"tf32x3": 3, "fp16x3": 3, "bf16x1": 1, "fp32_simt": 0}[args.precision]}
+                "mma_passes": {"tf32x3": 3, "fp16x3": 3, "bf16x1": 1, "fp32_simt": 0}[args.precision],
+                "issue_rate_frac_of_peak": fc_tflops * {"tf32x3": 3, "fp16x3": 3, "bf16x1": 1, "fp32_simt": 0}[args.precision] / peaks["bf16_tflops"],
+                "measured_on": "the profiled region (plain launches, nets back to back on one stream); the value region "
+                               "replays the same kernels as one graph with the two nets on two branches"}
     ls_gbs = LS_BYTES_PER_PKT * npkt / (ls_ms_per_step * 1e-3) / 1e9 if ls_ms_per_step > 0 else 0.0
     roofline_ls = {"bound": "hbm", "kernel": "ls_kernel", "achieved": ls_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": ls_gbs / peaks["hbm_gbs"], "avg_launch_ms": prof["ls_ms"] / max(1, prof["ls_launches"]),
-                   "traffic": (traffic.get("ls_kernel", {}).get("bytes_per_launch") if args.precision == "fp16x3" and npkt == 500 else None),
-                   "bytes_per_launch": LS_BYTES_PER_PKT * npkt,
-                   "note": "algorithmic bytes = Y in + one operand-plane set out (2 MiB/packet)"}
+                   "traffic": ls_traffic, "traffic_source": ls_src,
+                   "bytes_per_launch": LS_BYTES_PER_PKT * npkt / max(1, prof["ls_launches"] // args.steps),
+                   "note": "algorithmic bytes = Y in + one operand-plane set out"}
+    stage_ms_per_step = prof["stage_ms"] / args.steps
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,25 +483,37 @@ def run_ours(args):
                         "sample": "%d packets (torch-CPU c128 LS + fp32 FC, batch=Nt*Nr per predict), %.1f s" % (args.cpu_sample, dt)}
 
     if rank == 0:
+        io_gib = npkt * NT * NR * NSC * 8 / 2 ** 30
+        if world == 1:
+            launch_note = ("value: every step is ONE CUDA-graph launch per internal chunk (%d graph launches, %d kernels in the "
+                           "timed region)" % (graph_launches, launches))
+        else:
+            launch_note = ("value: plain stream launches (%d kernels in the timed region; the gathering schedule uses a side "
+                           "stream and is not graph-captured) + one 4-byte all-reduce per step" % launches)
         line = {
-            "metric": "channel-estimates/sec (32x4, 1024-sc pkts)", "value": value, "unit": "packets/s",
+            "metric": METRIC, "value": value, "unit": "packets/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"tf32x3": "tf32x3 split (fp32-grade), fp32 accumulate", "fp16x3": "fp16x3 split (fp32-grade), fp32 accumulate",
                       "bf16x1": "bf16", "fp32_simt": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pkts_per_gpu": npkt, "precision": args.precision,
-                       "l2": "inputs (0.5 GiB Y) and outputs (0.5 GiB) per step exceed the 126 MB L2",
-                       "launch": "value: one CUDA-graph launch per step (7 kernels); rooflines: the same K steps re-run after "
-                                 "1 s idle as plain launches with per-kernel CUDA events (ms_per_step_profiled)",
+            "config": {"workload": WORKLOAD},
+            "detail": {"pkts_per_gpu": npkt, "precision": args.precision,
+                       "fp16_operand_scale": "auto (per-call amax pre-pass + per-level device-side scales)" if args.precision == "fp16x3" else None,
+                       "l2": "inputs (%.2f GiB Y) and outputs (%.2f GiB) per step exceed the 126 MB L2" % (io_gib, io_gib),
+                       "launch": launch_note + "; rooflines: the same K steps re-run after 1 s idle as plain launches with "
+                                               "per-kernel CUDA events (ms_per_step_profiled)",
                        "numa_bind": numa_note,
                        "parallelism": "packets sharded over %d GPU(s)%s" % (
                            world, (", all-gather of H planes in step (%s)" % gather_note) if world > 1 else "")},
             "clocks": clocks,
-            "e2e": {"value": e2e_val if e2e_steps else None, "unit": "packets/s", "h2d_bytes_per_step": int(Yh.numel() * 8),
-                    "d2h_bytes_per_step": int(2 * rows * NSC * 4), "checksum": checksum},
-            "gpu_launches": int(launches), "graph_launches": int(eng.stats()["graph_launches"]),
+            "e2e": {"value": e2e_val, "unit": "packets/s", "h2d_bytes_per_step": int(e2e_n * NR * NT * NSC * 8),
+                    "d2h_bytes_per_step": int(2 * e2e_n * NT * NR * NSC * 4), "checksum": checksum, "pkts_per_step": e2e_n,
+                    "copy_ceiling_gbs": ceiling,
+                    "achieved_gbs_each_way": (e2e_val / world * NR * NT * NSC * 8 / 1e9) if e2e_val else None},
+            "gpu_launches": int(launches), "graph_launches": int(graph_launches),
             "roofline": roofline, "roofline_ls": roofline_ls,
+            "amax_prepass_ms_per_step": stage_ms_per_step,
             "pair_estimates_per_s": value * NT * NR, "us_per_packet": 1e6 / value,
             "ms_per_step_profiled": ms_prof_step,
         }
@@ -409,6 +521,8 @@ def run_ours(args):
             line["value_compute_only"] = value_compute_only
         if gather_check is not None:
             line["fused_gather_equals_nccl"] = gather_check
+        if parity is not None:
+            line["parity"] = parity
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -433,22 +547,28 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how H-hat is all-gathered")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
-    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
-                    help="c2 = BASELINE configs[1] (the bench line); c5 = configs[4]: Nt64 Nr8 2048 sc, 3000 packets per GPU "
-                         "processed as 24 steps of 125 with the fused all-gather (gathered chunk consumed/overwritten per step)")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer region (c5: 1 GB of pinned buffers per rank)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2] (3000 packets, 8 SNR levels); c4 = configs[3] "
+                         "(Nt64 Nr8 2048 sc, 3000 packets); c5 = configs[4]: 3000 packets per GPU processed as 24 steps of 125 with "
+                         "the fused all-gather (gathered chunk consumed/overwritten per step)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer region")
+    ap.add_argument("--e2e-pkts", type=int, default=0, help="packets per end-to-end step (default: the batch, c4: 250)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison after the timed regions")
     args = ap.parse_args()
-    if args.config == "c5":
-        global NT, NR, NSC, WORKLOAD, MLP_FLOP_PER_PKT, LS_BYTES_PER_PKT
-        NT, NR, NSC = 64, 8, 2048
-        WORKLOAD = ("configs[4]: Nt=64 Nr=8, 2048 sc, 3000 packets per GPU as chunks of %d per step, FC 2048-1024-1024-2048 x2 nets, "
-                    "all-gather of H-hat per chunk" % (125 if args.npkt == 500 else args.npkt))
-        MLP_FLOP_PER_PKT = NT * NR * 2 * 2 * (NSC * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * NSC)
-        LS_BYTES_PER_PKT = NR * NT * NSC * 8 * 2
-        if args.npkt == 500:
-            args.npkt = 125
+    global NT, NR, NSC, WORKLOAD, METRIC, MLP_FLOP_PER_PKT, LS_BYTES_PER_PKT, SNR_LEVELS
+    c = CONFIGS[args.config]
+    NT, NR, NSC, WORKLOAD, METRIC, SNR_LEVELS = c["nt"], c["nr"], c["nsc"], c["workload"], c["metric"], c.get("snr_levels")
+    MLP_FLOP_PER_PKT = NT * NR * 2 * 2 * (NSC * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * NSC)
+    LS_BYTES_PER_PKT = NR * NT * NSC * 8 * 2
+    if args.npkt == 500:
+        args.npkt = c["npkt"]
+    if not args.e2e_pkts:
+        args.e2e_pkts = c["e2e_pkts"] or 0
+    if args.config in ("c4", "c5"):
         args.gen_pkts = min(args.gen_pkts, 5)
         args.cpu_sample = min(args.cpu_sample, 16)
+    if args.config == "c3":
+        args.gen_pkts = max(8, args.gen_pkts // 8 * 8)          # whole cycles of the 8 SNR levels
     # the synth module is pure numpy: load it standalone so the reference arm never touches the CUDA library
     import importlib.util
     spec = importlib.util.spec_from_file_location(

@@ -51,14 +51,15 @@ SYMBOLS = [
     "mamimo_create", "mamimo_destroy", "mamimo_set_pilots", "mamimo_load_layer", "mamimo_finalize_weights",
     "mamimo_ls_estimate", "mamimo_estimate", "mamimo_estimate_stages", "mamimo_predict_planes", "mamimo_predict_time",
     "mamimo_synchronize", "mamimo_poll_flags", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
-    "mamimo_profile_begin", "mamimo_profile_end",
+    "mamimo_profile_begin", "mamimo_profile_end", "mamimo_get_debug_counters",
     "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time", "mamimo_lmmse", "mamimo_tau_rms",
     "mamimo_gather_create", "mamimo_gather_connect", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
 ]
 
 
 def _load():
-    path = _build.LIB_PATH
+    # MAMIMO_LIB: an alternative build of the same library (e.g. the -DMAMIMO_FC_DEBUG_COUNTERS one tools/fc_power_probe.py uses)
+    path = os.environ.get("MAMIMO_LIB") or _build.LIB_PATH
     if not os.path.exists(path):
         raise ImportError(
             "%s is missing: the CUDA library is the product and there is no CPU fallback. "
@@ -99,6 +100,7 @@ def _load():
         "mamimo_ipc_export": (i32, [vp, C.c_char_p]),
         "mamimo_ipc_open": (i32, [C.c_char_p, C.POINTER(vp)]),
         "mamimo_ipc_close": (i32, [vp]),
+        "mamimo_get_debug_counters": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "mamimo_profile_begin": (i32, [vp]),
         "mamimo_profile_end": (i32, [vp, C.POINTER(Profile)]),
     }

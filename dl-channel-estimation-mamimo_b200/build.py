@@ -58,27 +58,39 @@ def _nvcc():
     raise RuntimeError("nvcc not found: cannot build the sm_100a library")
 
 
-def is_stale():
-    if not os.path.exists(LIB_PATH):
+def is_stale(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+DEBUG_LIB_PATH = os.path.join(PKG_DIR, "libmamimo_b200_dbg.so")   # -DMAMIMO_FC_DEBUG_COUNTERS build (diagnostics only)
+
+
+def build_debug(force=False):
+    """The same library with the FC role counters compiled in (tools/fc_power_probe.py loads it via MAMIMO_LIB)."""
+    if not force and os.path.exists(DEBUG_LIB_PATH) and not is_stale(DEBUG_LIB_PATH):
+        return DEBUG_LIB_PATH
+    return build(force=True, extra=["-DMAMIMO_FC_DEBUG_COUNTERS"], out=DEBUG_LIB_PATH)
+
+
+def build(force=False, verbose=False, extra=None, out=None):
     """Compile the library if missing or older than its sources.  Returns the .so path."""
-    if not force and not is_stale():
-        return LIB_PATH
-    extra = os.environ.get("MAMIMO_NVCC_EXTRA", "").split()      # e.g. -DMAMIMO_FC_DEBUG_COUNTERS
+    out = out or LIB_PATH
+    if not force and not is_stale(out):
+        return out
+    extra = list(extra or []) + os.environ.get("MAMIMO_NVCC_EXTRA", "").split()      # e.g. -DMAMIMO_FC_DEBUG_COUNTERS
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -1818,6 +1818,17 @@ mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* out) {
   return MAMIMO_OK;
 }
 
+mamimo_status mamimo_get_debug_counters(mamimo_engine* e, uint64_t out[8], int32_t reset) {
+  if (!e || !out) return MAMIMO_ERR_INVALID;
+  memset(out, 0, 8 * sizeof(uint64_t));
+  if (!e->d_dbg) return fail(e, MAMIMO_ERR_STATE, "role counters are off: set MAMIMO_FC_DEBUG=1 before mamimo_create on a library built with -DMAMIMO_FC_DEBUG_COUNTERS");
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaDeviceSynchronize());
+  CK(e, cudaMemcpy(out, e->d_dbg, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) CK(e, cudaMemset(e->d_dbg, 0, 8 * sizeof(uint64_t)));
+  return MAMIMO_OK;
+}
+
 mamimo_status mamimo_profile_begin(mamimo_engine* e) {
   if (!e) return MAMIMO_ERR_INVALID;
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

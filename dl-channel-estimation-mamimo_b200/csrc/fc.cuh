@@ -521,6 +521,7 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         uint32_t unit = 0;
         long long w_tempty = 0, w_full = 0;
         const long long dbg_t0 = MM_DBG(a) ? clock64() : 0;
+        const unsigned long long dbg_g0 = MM_DBG(a) ? globaltimer_ns() : 0ull;
         for (int tile = cluster_id; tile < total_tiles && ok; tile += n_clusters) {
           for (int c = 0; c < n_chunks && ok; ++c, ++unit) {
             const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
@@ -559,6 +560,8 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           atomicAdd(a.dbg + 3, static_cast<unsigned long long>(w_full));                 // MMA: waiting for operands
           atomicAdd(a.dbg + 4, static_cast<unsigned long long>(clock64() - dbg_t0));     // MMA: total
           atomicAdd(a.dbg + 5, 1ull);                                                    // clusters counted
+          atomicAdd(a.dbg + 6, globaltimer_ns() - dbg_g0);                               // MMA: total in ns (wall) ->
+                                                                                         // dbg[4] / dbg[6] = SM clock in GHz
         }
       }
     }

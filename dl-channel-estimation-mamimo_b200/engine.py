@@ -370,6 +370,12 @@ class Engine:
               self._h)
         return out
 
+    def debug_counters(self, reset=True):
+        """role counters of the CTA-pair FC kernel (mamimo_get_debug_counters; debug build + MAMIMO_FC_DEBUG=1)"""
+        out = (C.c_uint64 * 8)()
+        check(lib.mamimo_get_debug_counters(self._h, out, 1 if reset else 0), self._h)
+        return [int(v) for v in out]
+
     def synchronize(self):
         check(lib.mamimo_synchronize(self._h), self._h)
 

@@ -250,6 +250,13 @@ MAMIMO_API mamimo_status mamimo_get_stats(const mamimo_engine* e, mamimo_stats* 
 MAMIMO_API mamimo_status mamimo_profile_begin(mamimo_engine* e);
 MAMIMO_API mamimo_status mamimo_profile_end(mamimo_engine* e, mamimo_profile* out);
 
+/* Diagnostics (library built with -DMAMIMO_FC_DEBUG_COUNTERS, engine created with MAMIMO_FC_DEBUG=1 in the environment;
+ * MAMIMO_ERR_STATE otherwise).  Sums over the CTA-pair FC kernel's cluster-launches since the last reset:
+ * [0] producer cycles waiting for a free stage, [1] producer cycles total, [2] MMA-issuer cycles waiting for a drained
+ * TMEM buffer, [3] waiting for operands, [4] MMA-issuer cycles total, [5] cluster-launches, [6] MMA-issuer wall time in
+ * ns (globaltimer): [4] / [6] = the SM clock in GHz the kernel actually ran at, [7] unused. */
+MAMIMO_API mamimo_status mamimo_get_debug_counters(mamimo_engine* e, uint64_t out[8], int32_t reset);
+
 /* pinned host memory helpers for callers that want overlapped copies */
 MAMIMO_API void* mamimo_host_alloc(size_t bytes);
 MAMIMO_API void mamimo_host_free(void* p);

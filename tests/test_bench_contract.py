@@ -24,11 +24,20 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "packets/s"
     assert d["metric"].startswith("channel-estimates/sec") and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["config"]["workload"].startswith("configs[1]") and d["config"]["sample_pkts_per_step"] == 4
+    # `config` carries the workload only, so both arms print the SAME config dict (the driver compares them)
+    assert d["config"] == {"workload": d["config"]["workload"]} and d["config"]["workload"].startswith("configs[1]")
+    assert d["sample_pkts_per_step"] == 4
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "4 packets" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_configs_keep_metric_and_workload_in_step():
+    r = _run(["--impl", "reference", "--config", "c4", "--steps", "1", "--warmup", "0", "--cpu-sample", "1"])
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["metric"] == "channel-estimates/sec (64x8, 2048-sc pkts)" and d["config"]["workload"].startswith("configs[3]")
 
 
 def test_reference_arm_only_rank0_prints():
