@@ -399,7 +399,10 @@ def run_ours(args):
     # (2) parity: one gathered packet PER RANK against the FP64 oracle on rank 0 (N = 1: one packet of the batch)
     gather_check, parity = None, None
     if world > 1:
-        eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
+        if fused:       # same kernels, same schedule, local planes written too: NCCL-gather those and compare bit for bit
+            eng.estimate_stages_raw(ALL | eng.STAGE_GATHER, Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), stream.cuda_stream)
+        else:
+            eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
         dist.all_gather_into_tensor(gathered[0], Hr)
         dist.all_gather_into_tensor(gathered[1], Hi)
         barrier()

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,8 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 }  // namespace
+
+constexpr int kDynSlotsMax = 8;
 
 struct mamimo_engine {
   mamimo_config cfg;
@@ -123,7 +126,12 @@ struct mamimo_engine {
   // host-memory pipeline
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_side = nullptr;
   cudaEvent_t ev_side[2] = {nullptr, nullptr};
-  int gather_sms = 0;           // > 0: SMs given to the real net's gathering layer while the imaginary net computes
+  int gather_sms = 0;           // > 0: SMs given to the gathering final layers (side stream) while other work computes
+  int gather_sub = 1;           // > 1: pipelined step -- the batch is cut into this many sub-batches and the gathering
+                                // layers of sub-batch i run under LS + hidden layers of sub-batch i+1
+  int cur_row_off = 0;          // first pair row of the sub-batch being enqueued (operand buffers + gather slot)
+  int ls_sm_limit = 0;          // > 0: SMs the LS kernel may fill (the rest hold gathering CTAs)
+  cudaEvent_t ev_sub[kDynSlotsMax] = {};
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   void* st_in[2] = {nullptr, nullptr};
   size_t st_in_bytes = 0;
@@ -235,7 +243,7 @@ mamimo_status make_map(mamimo_engine* e, CUtensorMap* map, const Operand& op, in
 }
 
 constexpr int kTcBN = 256;
-constexpr int kDynSlots = 8;
+constexpr int kDynSlots = kDynSlotsMax;
 static_assert(kMaxLevels >= MAMIMO_MAX_HIDDEN + 1, "DynState levels");
 
 DynState* dyn_of(mamimo_engine* e) {
@@ -375,7 +383,8 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
   const int n_tiles = (a.n_sc + 63) / 64;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   const int per_sm = std::max(1, std::min(e->ls_tma_ctas, (227 * 1024) / (smem + 1024)));
-  const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(e->num_sms) * per_sm));
+  const int sms = e->ls_sm_limit > 0 ? std::min(e->ls_sm_limit, e->num_sms) : e->num_sms;
+  const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(sms) * per_sm));
   {
     ProfScope ps(e, st, kClsLs);
     ls_tma_kernel<S, NLTF, STAGES, NPS><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
@@ -469,6 +478,9 @@ mamimo_status run_mlp(mamimo_engine* e, int n_rows, float* out_r, float* out_i, 
       a.dbg = e->d_dbg;
       a.dyn = dyn_of(e); a.net = net; a.level = l; a.fixed_scale = e->dyn_fixed ? 1 : 0;
       a.w_inv_scale = 1.0f / d.w_scale; a.rowsum = d.rowsum; a.bmax = d.bmax;
+      a.row_off = e->cur_row_off;
+      if (a.row_off && (S == kFp32Simt || !e->fc_pair || (a.row_off % (2 * kFcBlockM))))
+        return fail(e, MAMIMO_ERR_UNSUPPORTED, "sub-batch row offsets need the CTA-pair kernel and 256-row alignment");
       a.A = reinterpret_cast<const float*>(A.ptr); a.W = reinterpret_cast<const float*>(d.w.ptr); a.kpad = d.K;
       if (last) {
         a.out_f32 = net == 0 ? out_r : out_i;
@@ -534,6 +546,7 @@ mamimo_status run_ls(mamimo_engine* e, const void* dY, int y_double, int n_pkt, 
   a.pil_per_tile = std::max(1, 128 / e->cfg.n_ps);
   a.y_double = y_double; a.h_double = h_double; a.flags = e->d_flags;
   a.dyn = want_planes ? dyn_of(e) : nullptr; a.in_gain = e->ls_gain; a.fixed_scale = e->dyn_fixed ? 1 : 0;
+  a.row_off = want_planes ? e->cur_row_off : 0;
   return launch_ls<S>(e, a, st);
 }
 
@@ -648,12 +661,12 @@ mamimo_status make_gather_maps(mamimo_engine* e, int net, int n_rows, GatherMaps
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (e->gather_world < 1) return fail(e, MAMIMO_ERR_STATE, "fused all-gather not connected (mamimo_gather_connect)");
-  if (n_rows > e->gather_rows) return fail(e, MAMIMO_ERR_INVALID, "more rows than the gather slot holds");
+  if (e->cur_row_off + n_rows > e->gather_rows) return fail(e, MAMIMO_ERR_INVALID, "more rows than the gather slot holds");
   const int d_out = e->cfg.d_out;
   if (d_out % 4) return fail(e, MAMIMO_ERR_UNSUPPORTED, "fused all-gather needs d_out % 4 == 0 (TMA row pitch)");
   memset(gm, 0, sizeof(*gm));
   for (int p = 0; p < e->gather_world; ++p) {
-    float* base = e->gather_peer[net][p] + static_cast<size_t>(e->gather_rank) * e->gather_rows * d_out;
+    float* base = e->gather_peer[net][p] + (static_cast<size_t>(e->gather_rank) * e->gather_rows + e->cur_row_off) * d_out;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_out), static_cast<cuuint64_t>(n_rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_out) * sizeof(float)};
     const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kFcBlockM)};
@@ -1033,6 +1046,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   ck(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking), "stream");
   ck(cudaStreamCreateWithFlags(&e->s_side, cudaStreamNonBlocking), "stream");
   for (int i = 0; i < 2; ++i) ck(cudaEventCreateWithFlags(&e->ev_side[i], cudaEventDisableTiming), "event");
+  for (int i = 0; i < kDynSlotsMax; ++i) ck(cudaEventCreateWithFlags(&e->ev_sub[i], cudaEventDisableTiming), "event");
   for (int i = 0; i < 2; ++i) {
     ck(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming), "event");
     ck(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming), "event");
@@ -1117,6 +1131,7 @@ void mamimo_destroy(mamimo_engine* e) {
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   if (e->s_side) cudaStreamDestroy(e->s_side);
   for (int i = 0; i < 2; ++i) if (e->ev_side[i]) cudaEventDestroy(e->ev_side[i]);
+  for (int i = 0; i < kDynSlotsMax; ++i) if (e->ev_sub[i]) cudaEventDestroy(e->ev_sub[i]);
   for (int i = 0; i < 4; ++i) if (e->lm_ev[i]) cudaEventDestroy(e->lm_ev[i]);
   delete e;
 }
@@ -1295,8 +1310,56 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
   const size_t hlsb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.n_sc * 8;
   const size_t hb = static_cast<size_t>(e->rows_per_pkt) * e->cfg.d_out * sizeof(float);
+  // packets per 256-row pair tile: sub-batch boundaries must fall on whole tiles
+  const int pkt_align = (2 * kFcBlockM) / std::gcd(2 * kFcBlockM, e->rows_per_pkt);
+  const bool tc_pair = e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT;
+  const bool pipelined = gather && stages == all && e->gather_sub > 1 && e->gather_sms > 0 && e->n_layers >= 2 && tc_pair &&
+                         n_pkt >= 2LL * pkt_align;
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
     mamimo_status s = MAMIMO_OK;
+    if (pipelined) {
+      // Pipelined fused all-gather.  The batch is cut into sub-batches that live side by side in the operand buffers
+      // (row offsets); LS + hidden layers of sub-batch i+1 run on `st` while the gathering final layers of sub-batch
+      // i -- the kernels whose epilogue TMA-stores every tile into every rank's plane over NVLink -- run on the side
+      // stream with gather_sms SMs, so the links are busy from the end of the first sub-batch to the end of the step.
+      const int L = e->n_layers, full = e->fc_sms, g = e->gather_sms;
+      const int64_t units = (n + pkt_align - 1) / pkt_align;
+      const int S = static_cast<int>(std::min<int64_t>(std::min(e->gather_sub, kDynSlotsMax), units));
+      // the first sub-batch is the short one (NVLink idles until it is through), the rest are equal
+      int64_t first_u = std::max<int64_t>(1, units / (2 * S));
+      if (S == 1) first_u = units;
+      int64_t pkt0 = 0;
+      for (int i = 0; i < S && s == MAMIMO_OK; ++i) {
+        const int64_t rest_u = units - first_u;
+        const int64_t u = i == 0 ? first_u : (rest_u / (S - 1) + (i - 1 < rest_u % (S - 1) ? 1 : 0));
+        const int64_t np_i = std::min<int64_t>(u * pkt_align, n - pkt0);
+        if (np_i <= 0) break;
+        const int rows_i = static_cast<int>(np_i) * e->rows_per_pkt;
+        e->dyn_slot = i;
+        e->cur_row_off = static_cast<int>(pkt0) * e->rows_per_pkt;
+        const char* y_i = static_cast<const char*>(in0) + pkt0 * yb;
+        void* hls_i = hls ? static_cast<char*>(hls) + pkt0 * hlsb : nullptr;
+        float* hr_i = hr ? hr + static_cast<size_t>(e->cur_row_off) * e->cfg.d_out : nullptr;
+        float* hi_i = hi ? hi + static_cast<size_t>(e->cur_row_off) * e->cfg.d_out : nullptr;
+        e->fc_sms = i == 0 ? full : full - g;                 // nothing runs on the side stream during the first one
+        e->ls_sm_limit = i == 0 ? 0 : e->num_sms - g;
+        s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
+                      y_type == MAMIMO_C128, st);
+        if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_ls<S>(e, y_i, y_type == MAMIMO_C128, static_cast<int>(np_i), hls_i, 0, true, st)));
+        if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows_i, hr_i, hi_i, st, 3u, false, 0, L - 1)));
+        if (s != MAMIMO_OK) break;
+        CK(e, cudaEventRecord(e->ev_sub[i], st));
+        CK(e, cudaStreamWaitEvent(e->s_side, e->ev_sub[i], 0));
+        e->fc_sms = (i == S - 1 || pkt0 + np_i >= n) ? full : g;   // the last gather has the machine to itself
+        s = DISPATCH_S(e, (run_mlp<S>(e, rows_i, hr_i, hi_i, e->s_side, 3u, true, L - 1, L)));
+        pkt0 += np_i;
+      }
+      e->fc_sms = full; e->ls_sm_limit = 0; e->dyn_slot = 0; e->cur_row_off = 0;
+      if (s != MAMIMO_OK) return s;
+      CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
+      CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
+      return MAMIMO_OK;
+    }
     if (stages & MAMIMO_STAGE_LS) {
       s = dyn_begin(e, in0, static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
                     y_type == MAMIMO_C128, st);
@@ -1332,7 +1395,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   // Device-resident full path on a capturable stream: the 7 launches of a batch are captured once per
   // (buffers, batch size, stream) and replayed as ONE graph launch afterwards.
   cudaStream_t ust = static_cast<cudaStream_t>(stream);
-  if (mem == MAMIMO_MEM_DEVICE && stages == all && !gather && e->use_graphs && !e->profiling && ust != nullptr &&
+  if (mem == MAMIMO_MEM_DEVICE && stages == all && (!gather || pipelined) && e->use_graphs && !e->profiling && ust != nullptr &&
       ust != cudaStreamLegacy && ust != cudaStreamPerThread && n_pkt > 0) {
     cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(ust, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone) {
@@ -1490,6 +1553,9 @@ mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, 
   e->gather_sms = world >= 3 ? 56 : 0;     // measured: 4 GPUs 590 k pkt/s (512 k without), 8 GPUs 623 k (585 k with 36 SMs)
   if (const char* env = getenv("MAMIMO_GATHER_SMS")) e->gather_sms = atoi(env) & ~1;
   if (e->gather_sms >= e->fc_sms - 2) e->gather_sms = 0;
+  // pipelined step (sub-batches): NVLink busy under the next sub-batch's LS + hidden layers
+  e->gather_sub = world >= 3 ? 4 : 1;
+  if (const char* env = getenv("MAMIMO_GATHER_SUB")) e->gather_sub = std::max(1, std::min(atoi(env), kDynSlotsMax));
   return MAMIMO_OK;
 }
 

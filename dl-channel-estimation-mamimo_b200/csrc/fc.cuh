@@ -65,6 +65,8 @@ struct FcArgs {
   // publishes it as dyn->scale[net][level + 1] and the measured amax of its outputs as dyn->amax[net][level + 1].
   DynState* dyn;
   int net, level, fixed_scale;
+  int row_off;           // first row of this call inside the operand buffers (sub-batches of a pipelined step keep
+                         // their activations side by side in the same buffers); multiple of the 256-row pair tile
   float w_inv_scale;     // 1 / weight scale
   float rowsum;          // max_n sum_k |W[k][n]| (BN-folded), rounded up
   float bmax;            // max_n |bias[n]|
@@ -167,7 +169,7 @@ __device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const FcScale
 #pragma unroll
     for (int q = 0; q < Sch::kPlanes; ++q) {
       E* dst = reinterpret_cast<E*>(a.out_planes) +
-               (static_cast<size_t>(q) * a.out_plane_rows + row) * a.out_kpad + n0;
+               (static_cast<size_t>(q) * a.out_plane_rows + a.row_off + row) * a.out_kpad + n0;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int i = 0; i < kWords / 4; ++i)
@@ -256,7 +258,7 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
             for (int p = 0; p < kPlanes; ++p)
               tma_load_2d(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
-                          p * a.a_plane_rows + m_blk * kFcBlockM);
+                          p * a.a_plane_rows + a.row_off + m_blk * kFcBlockM);
 #pragma unroll
             for (int p = 0; p < kPlanes; ++p)
               tma_load_2d(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,
@@ -492,13 +494,13 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             if (next_row0 >= 0 && a.l2_prefetch) {
 #pragma unroll
               for (int p = 0; p < kPlanes; ++p)
-                tma_prefetch_l2_2d(&tmap_a, kb * Sch::kBlockK, p * a.a_plane_rows + next_row0);
+                tma_prefetch_l2_2d(&tmap_a, kb * Sch::kBlockK, p * a.a_plane_rows + a.row_off + next_row0);
             }
             if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);
 #pragma unroll
             for (int p = 0; p < kPlanes; ++p)
               tma_load_2d_pair(st + p * Cfg::kABytes, &tmap_a, full_bar + stage, kb * Sch::kBlockK,
-                               p * a.a_plane_rows + row0);
+                               p * a.a_plane_rows + a.row_off + row0);
 #pragma unroll
             for (int p = 0; p < kPlanes; ++p)
               tma_load_2d_pair(st + kPlanes * Cfg::kABytes + p * Cfg::kBBytes, &tmap_b, full_bar + stage,

@@ -38,6 +38,7 @@ struct LsArgs {
   DynState* dyn;
   float in_gain;          // bound on |H component| / amax|Y component| (P row sums, 1/|nltf x|, interpolation)
   int fixed_scale;
+  int row_off;            // first pair row of this call inside the operand planes (sub-batches of a pipelined step)
 };
 
 template <int S>
@@ -109,7 +110,7 @@ __device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, co
       Sch::split2(im[2], im[3], a.scale, i23, &ovf);
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
-        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + a.row_off + row) * a.kpad + k;
         *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[0]) + off) = make_uint2(r01[pl], r23[pl]);
         *reinterpret_cast<uint2*>(reinterpret_cast<E*>(a.planes[1]) + off) = make_uint2(i01[pl], i23[pl]);
       }
@@ -122,7 +123,7 @@ __device__ __forceinline__ void ls_store4(const LsArgs& a, size_t row, int k, co
       }
 #pragma unroll
       for (int pl = 0; pl < Sch::kPlanes; ++pl) {
-        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+        const size_t off = (static_cast<size_t>(pl) * a.plane_rows + a.row_off + row) * a.kpad + k;
         E* d0 = reinterpret_cast<E*>(a.planes[0]) + off;
         E* d1 = reinterpret_cast<E*>(a.planes[1]) + off;
         if constexpr (sizeof(E) == 4) {
@@ -197,7 +198,7 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
         Sch::split(h.y, a.scale, pi, &ovf);
 #pragma unroll
         for (int pl = 0; pl < Sch::kPlanes; ++pl) {
-          const size_t off = (static_cast<size_t>(pl) * a.plane_rows + row) * a.kpad + k;
+          const size_t off = (static_cast<size_t>(pl) * a.plane_rows + a.row_off + row) * a.kpad + k;
           reinterpret_cast<E*>(a.planes[0])[off] = pr[pl];
           reinterpret_cast<E*>(a.planes[1])[off] = pi[pl];
         }

@@ -691,9 +691,10 @@ def test_estimate_from_time_domain_reference_numerology():
 
 
 # ------------------------------------------------------------------------------ fused all-gather (final FC layer -> peers)
-@pytest.mark.parametrize("gather_sms", [0, 36])
-@pytest.mark.parametrize("nt,nr,nsc,hidden,pkts", [(8, 2, 128, (128, 64), (5, 3)), (32, 4, 1024, (1024, 1024), (3, 3))])
-def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sms, monkeypatch):
+@pytest.mark.parametrize("gather_sms,gather_sub", [(0, 1), (36, 1), (36, 3), (56, 8)])
+@pytest.mark.parametrize("nt,nr,nsc,hidden,pkts", [(8, 2, 128, (128, 64), (5, 3)), (32, 4, 1024, (1024, 1024), (3, 3)),
+                                                   (32, 4, 256, (256, 128), (9, 7)), (8, 2, 128, (128, 64), (70, 33))])
+def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sms, gather_sub, monkeypatch):
     """Two engines on one GPU act as two ranks: each runs the path on its packet shard with MAMIMO_STAGE_GATHER and
     the final FC kernels TMA-store every tile into BOTH ranks' gathered planes.  Both planes must equal the
     unsharded result bit for bit (rank r's rows at r * pkts_per_rank * Nt*Nr)."""
@@ -701,6 +702,10 @@ def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sm
     # gather_sms > 0 forces the NVLink-bound schedule (real net's gathering layer on a side stream with few SMs,
     # concurrent with the imaginary net's hidden layers) that the engine picks by itself for world >= 3
     monkeypatch.setenv("MAMIMO_GATHER_SMS", str(gather_sms))
+    # gather_sub > 1: pipelined step -- sub-batches side by side in the operand buffers, the gathering layers of
+    # sub-batch i on the side stream under LS + hidden layers of sub-batch i+1 (needs >= 2 pair tiles of packets:
+    # the two larger cases; the small ones fall back to the one-shot schedules)
+    monkeypatch.setenv("MAMIMO_GATHER_SUB", str(gather_sub))
     x = mm.synth.make_pilots(nsc)
     nets = mm.synth.make_nets(nsc, hidden, nsc)
     npkt = sum(pkts)
