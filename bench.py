@@ -371,6 +371,8 @@ def run_ours(args):
     time.sleep(1.0)
     for _ in range(3):
         step_device()
+    if args.timeline and rank == 0:
+        os.environ["MAMIMO_TIMELINE"] = args.timeline      # rank 0's per-launch start/end times of the profiled region
     eng.profile_begin()
     barrier()
     ev0.record(stream)
@@ -380,6 +382,7 @@ def run_ours(args):
     barrier()
     ms_prof_step = ev0.elapsed_time(ev1) / args.steps
     prof = eng.profile_end()
+    os.environ.pop("MAMIMO_TIMELINE", None)
 
     # compute-only (no all-gather) for N > 1, reported beside value
     value_compute_only = None
@@ -400,6 +403,8 @@ def run_ours(args):
     gather_check, parity = None, None
     if world > 1:
         if fused:       # same kernels, same schedule, local planes written too: NCCL-gather those and compare bit for bit
+            Hr.zero_(); Hi.zero_(); g_real.zero_(); g_imag.zero_()      # a skipped or late write must show, not hide behind
+            barrier()                                                   # an equal value left by an earlier step
             eng.estimate_stages_raw(ALL | eng.STAGE_GATHER, Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), stream.cuda_stream)
         else:
             eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, stream.cuda_stream)
@@ -407,7 +412,17 @@ def run_ours(args):
         dist.all_gather_into_tensor(gathered[1], Hi)
         barrier()
         if fused:
-            ok = torch.tensor([int(torch.equal(gathered[0], g_real) and torch.equal(gathered[1], g_imag))], device=dev)
+            same = torch.equal(gathered[0], g_real) and torch.equal(gathered[1], g_imag)
+            if not same:        # say where: rows of which rank's slot differ (diagnostics on stderr, every rank)
+                for name, a, b in (("real", gathered[0], g_real), ("imag", gathered[1], g_imag)):
+                    bad = (a != b).any(dim=1).nonzero().flatten()
+                    if bad.numel():
+                        slots = torch.unique(bad // rows).tolist()
+                        sys.stderr.write("[rank %d] fused != nccl on the %s plane: %d rows, slots %s, first %d last %d, max |diff| %.3e; "
+                                         "all-zero rows among them: nccl %d, fused %d\n"
+                                         % (rank, name, bad.numel(), slots, int(bad[0]), int(bad[-1]), float((a - b).abs().max()),
+                                            int((a[bad] == 0).all(dim=1).sum()), int((b[bad] == 0).all(dim=1).sum())))
+            ok = torch.tensor([int(same)], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             gather_check = bool(ok.item())
     if rank == 0 and not args.no_parity_check:
@@ -491,8 +506,8 @@ def run_ours(args):
             launch_note = ("value: every step is ONE CUDA-graph launch per internal chunk (%d graph launches, %d kernels in the "
                            "timed region)" % (graph_launches, launches))
         else:
-            launch_note = ("value: plain stream launches (%d kernels in the timed region; the gathering schedule uses a side "
-                           "stream and is not graph-captured) + one 4-byte all-reduce per step" % launches)
+            launch_note = ("value: %d kernels in the timed region (two streams: the gathering layers run on a side stream), issued as "
+                           "%d CUDA-graph launches, + one 4-byte all-reduce per step" % (launches, graph_launches))
         line = {
             "metric": METRIC, "value": value, "unit": "packets/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
@@ -557,6 +572,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer region")
     ap.add_argument("--e2e-pkts", type=int, default=0, help="packets per end-to-end step (default: the batch, c4: 250)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison after the timed regions")
+    ap.add_argument("--timeline", default="", help="write rank 0's per-launch timeline of the profiled region to this CSV")
     args = ap.parse_args()
     global NT, NR, NSC, WORKLOAD, METRIC, MLP_FLOP_PER_PKT, LS_BYTES_PER_PKT, SNR_LEVELS
     c = CONFIGS[args.config]

@@ -127,6 +127,11 @@ struct mamimo_engine {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_side = nullptr;
   cudaEvent_t ev_side[2] = {nullptr, nullptr};
   int gather_sms = 0;           // > 0: SMs given to the gathering final layers (side stream) while other work computes
+  double gather_growth = 1.2;   // size ratio of consecutive sub-batches (see mamimo_estimate_stages)
+  bool gather_ce = false;       // MAMIMO_GATHER_MODE=ce: the sub-batches' planes travel by copy engine (peer memcpy on per-peer
+                                // streams) instead of TMA stores from the final-layer kernels; SMs only compute
+  cudaStream_t s_copy[kMaxGatherRanks] = {};
+  cudaEvent_t ev_copy[kMaxGatherRanks] = {};
   int gather_sub = 1;           // > 1: pipelined step -- the batch is cut into this many sub-batches and the gathering
                                 // layers of sub-batch i run under LS + hidden layers of sub-batch i+1
   int cur_row_off = 0;          // first pair row of the sub-batch being enqueued (operand buffers + gather slot)
@@ -156,6 +161,7 @@ struct mamimo_engine {
   // CUDA-graph cache of the device-resident full path: one graph launch per batch (MAMIMO_GRAPH=0 disables)
   struct GraphEntry {
     const void* y; void* hls; float* hr; float* hi; int64_t n_pkt; int y_type; cudaStream_t st;
+    uint32_t mode;                      // stage mask incl. MAMIMO_STAGE_GATHER: a gathering graph is not a plain one
     cudaGraphExec_t exec; uint64_t launches; uint64_t stamp;
   };
   std::vector<GraphEntry> graphs;
@@ -165,7 +171,7 @@ struct mamimo_engine {
   uint64_t graph_stamp = 0, graph_replays = 0;
   mamimo_stats stats;
   // optional per-kernel-class device timing (mamimo_profile_begin/end)
-  struct ProfRec { cudaEvent_t a, b; int cls; };
+  struct ProfRec { cudaEvent_t a, b; int cls; cudaStream_t st; };
   std::vector<ProfRec> prof;
   bool profiling = false;
 };
@@ -196,7 +202,7 @@ struct ProfScope {
   mamimo_engine* e; cudaStream_t st; int idx = -1;
   ProfScope(mamimo_engine* e_, cudaStream_t st_, int cls) : e(e_), st(st_) {
     if (!e->profiling) return;
-    mamimo_engine::ProfRec r; r.cls = cls;
+    mamimo_engine::ProfRec r; r.cls = cls; r.st = st_;
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, st);
     e->prof.push_back(r);
@@ -1132,6 +1138,10 @@ void mamimo_destroy(mamimo_engine* e) {
   if (e->s_side) cudaStreamDestroy(e->s_side);
   for (int i = 0; i < 2; ++i) if (e->ev_side[i]) cudaEventDestroy(e->ev_side[i]);
   for (int i = 0; i < kDynSlotsMax; ++i) if (e->ev_sub[i]) cudaEventDestroy(e->ev_sub[i]);
+  for (int p = 0; p < kMaxGatherRanks; ++p) {
+    if (e->s_copy[p]) cudaStreamDestroy(e->s_copy[p]);
+    if (e->ev_copy[p]) cudaEventDestroy(e->ev_copy[p]);
+  }
   for (int i = 0; i < 4; ++i) if (e->lm_ev[i]) cudaEventDestroy(e->lm_ev[i]);
   delete e;
 }
@@ -1313,8 +1323,9 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   // packets per 256-row pair tile: sub-batch boundaries must fall on whole tiles
   const int pkt_align = (2 * kFcBlockM) / std::gcd(2 * kFcBlockM, e->rows_per_pkt);
   const bool tc_pair = e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT;
-  const bool pipelined = gather && stages == all && e->gather_sub > 1 && e->gather_sms > 0 && e->n_layers >= 2 && tc_pair &&
-                         n_pkt >= 2LL * pkt_align;
+  const bool ce_mode = gather && stages == all && e->gather_ce && tc_pair && e->n_layers >= 1;
+  const bool pipelined = ce_mode || (gather && stages == all && e->gather_sub > 1 && e->gather_sms > 0 && e->n_layers >= 2 &&
+                                     tc_pair && n_pkt >= 2LL * pkt_align);
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
     mamimo_status s = MAMIMO_OK;
     if (pipelined) {
@@ -1325,14 +1336,28 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
       const int L = e->n_layers, full = e->fc_sms, g = e->gather_sms;
       const int64_t units = (n + pkt_align - 1) / pkt_align;
       const int S = static_cast<int>(std::min<int64_t>(std::min(e->gather_sub, kDynSlotsMax), units));
-      // the first sub-batch is the short one (NVLink idles until it is through), the rest are equal
-      int64_t first_u = std::max<int64_t>(1, units / (2 * S));
-      if (S == 1) first_u = units;
+      // Sub-batch sizes grow geometrically (ratio gather_growth): the side stream moves a packet's planes at the NVLink
+      // rate, the main stream computes the next sub-batch's LS + hidden layers faster than that, so sub-batch i+1 may
+      // be larger than i by the ratio of the two rates without ever making the links wait -- and the first one, during
+      // which the links idle, is the smallest.
+      int64_t sizes[kDynSlotsMax];
+      {
+        const double r = e->gather_growth;
+        double w = 1.0, wsum = 0.0;
+        for (int i = 0; i < S; ++i) { wsum += w; w *= r; }
+        int64_t left = units;
+        w = 1.0;
+        for (int i = 0; i < S; ++i) {
+          int64_t u = i == S - 1 ? left : std::max<int64_t>(1, static_cast<int64_t>(units * w / wsum + 0.5));
+          u = std::min(u, left - (S - 1 - i));            // keep one unit for every later sub-batch
+          sizes[i] = std::max<int64_t>(u, 1);
+          left -= sizes[i];
+          w *= r;
+        }
+      }
       int64_t pkt0 = 0;
       for (int i = 0; i < S && s == MAMIMO_OK; ++i) {
-        const int64_t rest_u = units - first_u;
-        const int64_t u = i == 0 ? first_u : (rest_u / (S - 1) + (i - 1 < rest_u % (S - 1) ? 1 : 0));
-        const int64_t np_i = std::min<int64_t>(u * pkt_align, n - pkt0);
+        const int64_t np_i = std::min<int64_t>(sizes[i] * pkt_align, n - pkt0);
         if (np_i <= 0) break;
         const int rows_i = static_cast<int>(np_i) * e->rows_per_pkt;
         e->dyn_slot = i;
@@ -1341,6 +1366,31 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
         void* hls_i = hls ? static_cast<char*>(hls) + pkt0 * hlsb : nullptr;
         float* hr_i = hr ? hr + static_cast<size_t>(e->cur_row_off) * e->cfg.d_out : nullptr;
         float* hi_i = hi ? hi + static_cast<size_t>(e->cur_row_off) * e->cfg.d_out : nullptr;
+        if (ce_mode) {
+          // copy-engine variant: every layer of both nets on `st` with all SMs, the final layers writing straight into
+          // this rank's own slot of its gathered planes; then one peer memcpy per (plane, remote rank) on that rank's
+          // copy stream carries the sub-batch's rows over NVLink while the SMs start the next sub-batch
+          const size_t slot_off = (static_cast<size_t>(e->gather_rank) * e->gather_rows + e->cur_row_off) * e->cfg.d_out;
+          float* own_r = e->gather_local[0] + slot_off;
+          float* own_i = e->gather_local[1] + slot_off;
+          s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
+                        y_type == MAMIMO_C128, st);
+          if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_ls<S>(e, y_i, y_type == MAMIMO_C128, static_cast<int>(np_i), hls_i, 0, true, st)));
+          if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows_i, own_r, own_i, st, 3u, false, 0, L)));
+          if (s != MAMIMO_OK) break;
+          CK(e, cudaEventRecord(e->ev_sub[i], st));
+          const size_t bytes = static_cast<size_t>(rows_i) * e->cfg.d_out * sizeof(float);
+          for (int p = 0; p < e->gather_world; ++p) {
+            if (p == e->gather_rank) continue;
+            CK(e, cudaStreamWaitEvent(e->s_copy[p], e->ev_sub[i], 0));
+            CK(e, cudaMemcpyAsync(e->gather_peer[0][p] + slot_off, own_r, bytes, cudaMemcpyDeviceToDevice, e->s_copy[p]));
+            CK(e, cudaMemcpyAsync(e->gather_peer[1][p] + slot_off, own_i, bytes, cudaMemcpyDeviceToDevice, e->s_copy[p]));
+          }
+          if (hr_i) CK(e, cudaMemcpyAsync(hr_i, own_r, bytes, cudaMemcpyDeviceToDevice, st));
+          if (hi_i) CK(e, cudaMemcpyAsync(hi_i, own_i, bytes, cudaMemcpyDeviceToDevice, st));
+          pkt0 += np_i;
+          continue;
+        }
         e->fc_sms = i == 0 ? full : full - g;                 // nothing runs on the side stream during the first one
         e->ls_sm_limit = i == 0 ? 0 : e->num_sms - g;
         s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
@@ -1356,6 +1406,14 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
       }
       e->fc_sms = full; e->ls_sm_limit = 0; e->dyn_slot = 0; e->cur_row_off = 0;
       if (s != MAMIMO_OK) return s;
+      if (ce_mode) {
+        for (int p = 0; p < e->gather_world; ++p) {
+          if (p == e->gather_rank) continue;
+          CK(e, cudaEventRecord(e->ev_copy[p], e->s_copy[p]));
+          CK(e, cudaStreamWaitEvent(st, e->ev_copy[p], 0));
+        }
+        return MAMIMO_OK;
+      }
       CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
       CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
       return MAMIMO_OK;
@@ -1395,13 +1453,14 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   // Device-resident full path on a capturable stream: the 7 launches of a batch are captured once per
   // (buffers, batch size, stream) and replayed as ONE graph launch afterwards.
   cudaStream_t ust = static_cast<cudaStream_t>(stream);
+  const uint32_t graph_mode = stages | (gather ? MAMIMO_STAGE_GATHER : 0u);
   if (mem == MAMIMO_MEM_DEVICE && stages == all && (!gather || pipelined) && e->use_graphs && !e->profiling && ust != nullptr &&
       ust != cudaStreamLegacy && ust != cudaStreamPerThread && n_pkt > 0) {
     cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(ust, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone) {
       for (auto& g : e->graphs)
         if (g.y == Y && g.hls == H_ls && g.hr == H_real && g.hi == H_imag && g.n_pkt == n_pkt &&
-            g.y_type == static_cast<int>(y_type) && g.st == ust) {
+            g.y_type == static_cast<int>(y_type) && g.st == ust && g.mode == graph_mode) {
           g.stamp = ++e->graph_stamp;
           CK(e, cudaGraphLaunch(g.exec, ust));
           e->stats.kernel_launches += g.launches;
@@ -1426,7 +1485,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
         cudaGraphExecDestroy(e->graphs[lru].exec);
         e->graphs.erase(e->graphs.begin() + lru);
       }
-      e->graphs.push_back({Y, H_ls, H_real, H_imag, n_pkt, static_cast<int>(y_type), ust, exec,
+      e->graphs.push_back({Y, H_ls, H_real, H_imag, n_pkt, static_cast<int>(y_type), ust, graph_mode, exec,
                            e->stats.kernel_launches - l0, ++e->graph_stamp});
       CK(e, cudaGraphLaunch(exec, ust));
       e->stats.graph_launches++;
@@ -1554,8 +1613,17 @@ mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, 
   if (const char* env = getenv("MAMIMO_GATHER_SMS")) e->gather_sms = atoi(env) & ~1;
   if (e->gather_sms >= e->fc_sms - 2) e->gather_sms = 0;
   // pipelined step (sub-batches): NVLink busy under the next sub-batch's LS + hidden layers
-  e->gather_sub = world >= 3 ? 4 : 1;
+  if (const char* env = getenv("MAMIMO_GATHER_MODE")) e->gather_ce = strcmp(env, "ce") == 0;
+  if (e->gather_ce)
+    for (int p = 0; p < world; ++p) {
+      if (p == e->gather_rank || e->s_copy[p]) continue;
+      CK(e, cudaStreamCreateWithFlags(&e->s_copy[p], cudaStreamNonBlocking));
+      CK(e, cudaEventCreateWithFlags(&e->ev_copy[p], cudaEventDisableTiming));
+    }
+  e->gather_sub = world >= 5 ? 6 : (world >= 3 ? 8 : 1);
+  e->gather_growth = world >= 5 ? 1.8 : 1.2;
   if (const char* env = getenv("MAMIMO_GATHER_SUB")) e->gather_sub = std::max(1, std::min(atoi(env), kDynSlotsMax));
+  if (const char* env = getenv("MAMIMO_GATHER_GROWTH")) e->gather_growth = std::max(1.0, std::min(atof(env), 4.0));
   return MAMIMO_OK;
 }
 
@@ -1909,6 +1977,20 @@ mamimo_status mamimo_profile_end(mamimo_engine* e, mamimo_profile* out) {
   CK(e, cudaSetDevice(e->cfg.device));
   CK(e, cudaDeviceSynchronize());
   memset(out, 0, sizeof(*out));
+  if (const char* path = getenv("MAMIMO_TIMELINE")) {        // diagnostics: per-launch start/end (ms since the first launch)
+    if (FILE* f = e->prof.empty() ? nullptr : fopen(path, "w")) {
+      fprintf(f, "idx,class,stream,start_ms,end_ms\n");
+      int i = 0;
+      for (auto& r : e->prof) {
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventElapsedTime(&t0, e->prof[0].a, r.a) == cudaSuccess && cudaEventElapsedTime(&t1, e->prof[0].a, r.b) == cudaSuccess)
+          fprintf(f, "%d,%s,%s,%.4f,%.4f\n", i, r.cls == kClsLs ? "ls" : r.cls == kClsFc ? "fc" : r.cls == kClsLmmse ? "lmmse" : "stage",
+                  r.st == e->s_side ? "side" : "main", t0, t1);
+        ++i;
+      }
+      fclose(f);
+    }
+  }
   for (auto& r : e->prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
