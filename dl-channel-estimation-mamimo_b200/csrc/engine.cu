@@ -90,6 +90,9 @@ struct mamimo_engine {
   // FP16X3 range management (schemes.cuh): device-resolved per-level scales; dyn_fixed = act_scale_log2 pinned
   DynState* d_dyn = nullptr;    // [kDynSlots]; slot = sub-batch in flight
   bool dyn_fixed = false;
+  bool ls_verify = true;        // automatic scale: provisional + verify passes of the LS kernel (MAMIMO_LS_VERIFY=0: one pass
+                                // after an exact amax read of Y)
+  int ls_prof_cls = 0;          // profile class the LS launches are booked under (the verify pass counts as bookkeeping)
   int dyn_slot = 0;
   float ls_gain = 1.f;          // bound on |H_ls component| / amax |Y component|
   float tmax[2] = {0.f, 0.f};   // mode A: max |T| of the de-duplicated first layer
@@ -258,7 +261,7 @@ DynState* dyn_of(mamimo_engine* e) {
 
 // start of a call's range bookkeeping: zero the slot, then (auto mode) the exact amax of the input planes
 mamimo_status dyn_begin(mamimo_engine* e, const void* in0, size_t n0, const void* in1, size_t n1, bool is_double,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool may_sample = false) {
   DynState* d = dyn_of(e);
   if (!d) return MAMIMO_OK;
   CK(e, cudaMemsetAsync(d, 0, sizeof(DynState), st));
@@ -267,11 +270,19 @@ mamimo_status dyn_begin(mamimo_engine* e, const void* in0, size_t n0, const void
   const size_t cnt[2] = {n0, n1};
   for (int i = 0; i < 2; ++i) {
     if (!ptr[i] || !cnt[i]) continue;
-    const size_t vec = cnt[i] / (is_double ? 2 : 4);
+    // LS path (may_sample): large inputs are sampled 1 cache line in 8 -- the LS kernel's verify pass makes the result
+    // exact again (ls_resolve_scale); small ones and the staging paths read every element
+    const bool sample = may_sample && e->ls_verify && cnt[i] >= (static_cast<size_t>(1) << 22);
+    const size_t vec = cnt[i] / (is_double ? 2 : 4) / (sample ? 8 : 1);
     const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((vec + 255) / 256, static_cast<size_t>(e->num_sms) * 8)));
     ProfScope ps(e, st, kClsStage);
-    if (is_double) amax_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(ptr[i]), cnt[i], &d->in_amax[i]);
-    else amax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(ptr[i]), cnt[i], &d->in_amax[i]);
+    if (is_double) {
+      if (sample) amax_kernel<double, true><<<grid, 256, 0, st>>>(static_cast<const double*>(ptr[i]), cnt[i], &d->in_amax[i]);
+      else amax_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(ptr[i]), cnt[i], &d->in_amax[i]);
+    } else {
+      if (sample) amax_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float*>(ptr[i]), cnt[i], &d->in_amax[i]);
+      else amax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(ptr[i]), cnt[i], &d->in_amax[i]);
+    }
     CK(e, cudaGetLastError());
     e->stats.kernel_launches++;
   }
@@ -347,7 +358,7 @@ mamimo_status launch_ls_t(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
     CK(e, cudaFuncSetAttribute(ls_kernel<S, NLTF, HAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)));
   {
-    ProfScope ps(e, st, kClsLs);
+    ProfScope ps(e, st, e->ls_prof_cls);
     ls_kernel<S, NLTF, HAD><<<static_cast<unsigned>(grid), 128, smem, st>>>(a);
   }
   CK(e, cudaGetLastError());
@@ -361,7 +372,7 @@ mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st
   const long long grid = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   const size_t smem = static_cast<size_t>(NLTF) * (T + 4) * sizeof(float2);
   {
-    ProfScope ps(e, st, kClsLs);
+    ProfScope ps(e, st, e->ls_prof_cls);
     ls_had_split_kernel<S, NLTF, T><<<static_cast<unsigned>(grid), T * (NLTF / 16), smem, st>>>(a);
   }
   CK(e, cudaGetLastError());
@@ -392,7 +403,7 @@ mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) 
   const int sms = e->ls_sm_limit > 0 ? std::min(e->ls_sm_limit, e->num_sms) : e->num_sms;
   const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(sms) * per_sm));
   {
-    ProfScope ps(e, st, kClsLs);
+    ProfScope ps(e, st, e->ls_prof_cls);
     ls_tma_kernel<S, NLTF, STAGES, NPS><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
   }
   CK(e, cudaGetLastError());
@@ -553,7 +564,16 @@ mamimo_status run_ls(mamimo_engine* e, const void* dY, int y_double, int n_pkt, 
   a.y_double = y_double; a.h_double = h_double; a.flags = e->d_flags;
   a.dyn = want_planes ? dyn_of(e) : nullptr; a.in_gain = e->ls_gain; a.fixed_scale = e->dyn_fixed ? 1 : 0;
   a.row_off = want_planes ? e->cur_row_off : 0;
-  return launch_ls<S>(e, a, st);
+  a.pass = 0;
+  e->ls_prof_cls = kClsLs;
+  mamimo_status s = launch_ls<S>(e, a, st);
+  if (s != MAMIMO_OK || S != kFp16x3 || !a.dyn || e->dyn_fixed || !e->ls_verify) return s;
+  a.pass = 1;                      // verify the provisional scale against the exact amax; recomputes only if it must
+  a.H_ls = nullptr;                // H_ls itself never depends on the operand scale
+  e->ls_prof_cls = kClsStage;
+  s = launch_ls<S>(e, a, st);
+  e->ls_prof_cls = kClsLs;
+  return s;
 }
 
 template <int S>
@@ -1028,6 +1048,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_SMALL_OVERLAP")) { e->small_batch_overlap = atoi(env) != 0; e->always_overlap = atoi(env) != 1; }
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_VERIFY")) e->ls_verify = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;
@@ -1374,7 +1395,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
           float* own_r = e->gather_local[0] + slot_off;
           float* own_i = e->gather_local[1] + slot_off;
           s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
-                        y_type == MAMIMO_C128, st);
+                        y_type == MAMIMO_C128, st, true);
           if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_ls<S>(e, y_i, y_type == MAMIMO_C128, static_cast<int>(np_i), hls_i, 0, true, st)));
           if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows_i, own_r, own_i, st, 3u, false, 0, L)));
           if (s != MAMIMO_OK) break;
@@ -1394,7 +1415,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
         e->fc_sms = i == 0 ? full : full - g;                 // nothing runs on the side stream during the first one
         e->ls_sm_limit = i == 0 ? 0 : e->num_sms - g;
         s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
-                      y_type == MAMIMO_C128, st);
+                      y_type == MAMIMO_C128, st, true);
         if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_ls<S>(e, y_i, y_type == MAMIMO_C128, static_cast<int>(np_i), hls_i, 0, true, st)));
         if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_mlp<S>(e, rows_i, hr_i, hi_i, st, 3u, false, 0, L - 1)));
         if (s != MAMIMO_OK) break;
@@ -1420,7 +1441,7 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
     }
     if (stages & MAMIMO_STAGE_LS) {
       s = dyn_begin(e, in0, static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
-                    y_type == MAMIMO_C128, st);
+                    y_type == MAMIMO_C128, st, true);
       if (s != MAMIMO_OK) return s;
       s = DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, 0, true, st)));
     }
@@ -1741,7 +1762,7 @@ mamimo_status mamimo_estimate_time(mamimo_engine* e, const void* x, mamimo_ctype
     if (s != MAMIMO_OK) return s;
     if (mlp) {
       s = dyn_begin(e, e->d_ydemod, static_cast<size_t>(n) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
-                    false, st);
+                    false, st, true);
       if (s != MAMIMO_OK) return s;
     }
     s = DISPATCH_S(e, (run_ls<S>(e, e->d_ydemod, 0, static_cast<int>(n), hls, 0, mlp, st)));

@@ -39,20 +39,46 @@ struct LsArgs {
   float in_gain;          // bound on |H component| / amax|Y component| (P row sums, 1/|nltf x|, interpolation)
   int fixed_scale;
   int row_off;            // first pair row of this call inside the operand planes (sub-batches of a pipelined step)
+  int pass;               // automatic scale only: 0 = provisional pass, 1 = verify (and redo if needed) pass
+  int quiet_ovf;          // set by the kernel for pass 0: an overflow of the provisional scale is repaired by pass 1
 };
 
+// Level-0 scale of the FP16X3 planes.  Pinned scale: a.scale.  Automatic scale, without a full extra pass over Y:
+//   pass 0  uses a PROVISIONAL power of two from a sampled amax of Y (1 cache line in 8, every row of every slab) with
+//           one binade of headroom, measures the EXACT amax of the H_ls it emits, and keeps overflow quiet;
+//   pass 1  (the same kernel launched again) checks that exact amax against the provisional scale.  Inside the window
+//           [2^8, 60000] scaled -- no overflow happened, >= 11 binades above the fp16 residual floor -- every CTA returns
+//           at once (a ~3 us launch).  Otherwise the tiles are recomputed with the scale the exact amax calls for.
+// Either way the planes that layer 0 reads were written with a scale validated against the exact amax: correct for any
+// input, deterministic, and the common case costs 1/8 of a read of Y instead of a full one.
 template <int S>
-__device__ __forceinline__ float ls_resolve_scale(const LsArgs& a) {
+__device__ __forceinline__ float ls_resolve_scale(const LsArgs& a, bool& skip, int& quiet_ovf) {
+  skip = false;
+  quiet_ovf = 0;
   if constexpr (S == kFp16x3) {
     if (a.dyn && a.planes[0]) {
-      const float s = a.fixed_scale ? a.scale : pow2_scale_for(a.in_gain * __uint_as_float(a.dyn->in_amax[0]));
-      if (blockIdx.x == 0 && threadIdx.x == 0) { a.dyn->scale[0][0] = s; a.dyn->scale[1][0] = s; }
+      const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+      float s = a.scale;
+      if (!a.fixed_scale) {
+        if (a.pass == 0) {
+          s = pow2_scale_for(2.0f * a.in_gain * __uint_as_float(a.dyn->in_amax[0]));
+          quiet_ovf = 1;
+          if (writer) a.dyn->scale_prov = s;
+        } else {
+          const float amax = fmaxf(__uint_as_float(a.dyn->amax[0][0]), __uint_as_float(a.dyn->amax[1][0]));
+          const float sp = a.dyn->scale_prov;
+          const float v = amax * sp;
+          if ((v <= 60000.0f && v >= 256.0f) || amax == 0.0f) { skip = true; return sp; }
+          s = pow2_scale_for(amax * 1.000001f);
+        }
+      }
+      if (writer) { a.dyn->scale[0][0] = s; a.dyn->scale[1][0] = s; }
       return s;
     }
   }
+  if (a.pass != 0) skip = true;           // nothing to verify for the other schemes / pinned scales
   return a.scale;
 }
-
 
 template <int NLTF>
 __device__ __forceinline__ void fwht(float2 (&v)[NLTF]) {
@@ -205,7 +231,7 @@ __device__ __forceinline__ void ls_emit(const LsArgs& a, const float2* sh, int p
       }
     }
   }
-  if (ovf) atomicOr(a.flags, kFlagRange);
+  if (ovf && !a.quiet_ovf) atomicOr(a.flags, kFlagRange);
 }
 
 // HAD: P is Sylvester-Hadamard and n_tx == n_ltf == NLTF -> FWHT despread.  Otherwise a dense complex
@@ -217,7 +243,9 @@ __global__ void __launch_bounds__(128) ls_kernel(const LsArgs a_in) {
   using E = typename Sch::elem;
   extern __shared__ float2 sm_ls[];
   LsArgs a = a_in;
-  a.scale = ls_resolve_scale<S>(a_in);
+  bool skip;
+  a.scale = ls_resolve_scale<S>(a_in, skip, a.quiet_ovf);
+  if (skip) return;
   const int n_tiles = (a.n_pil + a.pil_per_tile - 1) / a.pil_per_tile;
   const int tile = blockIdx.x % n_tiles;
   const int prx = blockIdx.x / n_tiles;                 // pkt * n_rx + rx
@@ -311,6 +339,11 @@ template <int S, int NLTF, int T = 64>
 __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsArgs a) {
   constexpr int BLK = 16, NB = NLTF / BLK;
   extern __shared__ float2 sm_ls[];
+  LsArgs a2 = a;
+  a2.pil_per_tile = T;
+  bool skip;
+  a2.scale = ls_resolve_scale<S>(a, skip, a2.quiet_ovf);
+  if (skip) return;
   const int n_tiles = (a.n_pil + T - 1) / T;
   const int tile = blockIdx.x % n_tiles;
   const int prx = blockIdx.x / n_tiles;
@@ -344,9 +377,6 @@ __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsA
     }
   }
   __syncthreads();
-  LsArgs a2 = a;
-  a2.pil_per_tile = T;
-  a2.scale = ls_resolve_scale<S>(a);
   float amx[2] = {0.f, 0.f};
   ls_emit<S>(a2, sh, pitch, prx, pil0, pil0, amx);
   if (a.planes[0]) { publish_amax<S>(a.dyn, 0, 0, amx[0]); publish_amax<S>(a.dyn, 1, 0, amx[1]); }
@@ -375,6 +405,11 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
   float2* in = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(sm_ls_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint64_t* full = reinterpret_cast<uint64_t*>(in + STAGES * NLTF * TW);
   __shared__ uint32_t cta_abort;
+  LsArgs a2 = a;
+  a2.pil_per_tile = T;
+  bool skip;
+  a2.scale = ls_resolve_scale<S>(a, skip, a2.quiet_ovf);
+  if (skip) return;                                      // verify pass, provisional scale was inside the window
   const int n_tiles = (a.n_sc + T - 1) / T;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
   auto issue = [&](long long tile, int stage) {
@@ -397,9 +432,6 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
     }
   const int t = threadIdx.x & (T - 1);
   const int b = threadIdx.x / T;
-  LsArgs a2 = a;
-  a2.pil_per_tile = T;
-  a2.scale = ls_resolve_scale<S>(a);
   float amx[2] = {0.f, 0.f};
   long long it = 0;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
         }
         ls_store4<S>(a2, row0 + j, k0 + kk, re, im, ovf, amx);
       }
-      if (ovf) atomicOr(a.flags, kFlagRange);
+      if (ovf && !a2.quiet_ovf) atomicOr(a.flags, kFlagRange);
     }
     __syncthreads();                                     // stage consumed: refill it for the tile STAGES ahead
     if (threadIdx.x == 0) {
@@ -598,13 +630,16 @@ __global__ void expand_pairs_kernel(const float* __restrict__ Z, const float* __
 }
 
 // ---- amax pre-pass of the FP16X3 range management: max |component| of a float / double array ----------------
-template <typename T>
+// SAMPLE: read the first 128-byte line of every 1 KB (1 line in 8) -- only valid where a later stage verifies the
+// result against an exact amax (the LS path, ls_resolve_scale); false = every element.
+template <typename T, bool SAMPLE = false>
 __global__ void __launch_bounds__(256) amax_kernel(const T* __restrict__ p, size_t n, uint32_t* out_bits) {
   constexpr int V = 16 / sizeof(T);                      // elements per 16-byte load
   float m = 0.f;
-  const size_t nv = n / V;
+  const size_t nv = SAMPLE ? (n / V / 64) * 8 : n / V;   // sampled: 8 vectors out of every 64
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv; i += stride) {
+  for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < nv; j += stride) {
+    const size_t i = SAMPLE ? ((j >> 3) << 6) + (j & 7) : j;
     if constexpr (sizeof(T) == 4) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
       m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
@@ -613,7 +648,7 @@ __global__ void __launch_bounds__(256) amax_kernel(const T* __restrict__ p, size
       m = fmaxf(m, fmaxf(fabsf(static_cast<float>(v.x)), fabsf(static_cast<float>(v.y))));
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < n - nv * V) m = fmaxf(m, fabsf(static_cast<float>(p[nv * V + threadIdx.x])));
+  if (!SAMPLE && blockIdx.x == 0 && threadIdx.x < n - nv * V) m = fmaxf(m, fabsf(static_cast<float>(p[nv * V + threadIdx.x])));
   const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
   if ((threadIdx.x & 31) == 0 && w) atomicMax(out_bits, w);
 }

@@ -137,8 +137,10 @@ __host__ __device__ constexpr int pass_b(int i) { return i == 1 ? 1 : 0; }
 // act_scale_log2 != 0 pins one fixed scale instead (no pre-pass); then overflow AND underflow are flagged.
 constexpr int kMaxLevels = 9;            // activation levels per net: input of layer 0 .. input of layer 8
 struct DynState {
-  uint32_t in_amax[2];                   // float bits: amax of the raw input feeding net 0 / net 1 (LS: [0] only)
-  uint32_t pad[2];
+  uint32_t in_amax[2];                   // float bits: amax of the raw input feeding net 0 / net 1 (LS: [0] only; for large
+                                         // Y a 1-in-8 cache-line SAMPLE: see ls_resolve_scale for why that is still exact)
+  float scale_prov;                      // LS: provisional level-0 scale of pass 0
+  uint32_t pad;
   uint32_t amax[2][kMaxLevels];          // float bits: measured amax of the level's (unscaled) activations
   float scale[2][kMaxLevels];            // scale the level's operand planes were written with
 };

@@ -320,6 +320,36 @@ def test_amplitude_sweep_full_path(precision, gain, bias):
     assert rel_l2(ref_r, Hr) <= TOL_DNN and rel_l2(ref_i, Hi) <= TOL_DNN, (rel_l2(ref_r, Hr), rel_l2(ref_i, Hi))
 
 
+@pytest.mark.parametrize("spike", [3e4, 1.0, 1e-4])
+def test_ls_provisional_scale_is_verified_and_repaired(spike):
+    """Automatic fp16 scale on a batch large enough for the SAMPLED amax pre-pass (1 cache line in 8): a spike that only
+    lives in tones the sample never reads makes the provisional scale overflow (or, scaled the other way, sit far too
+    low); the LS kernel's verify pass must notice from the exact amax and recompute -- same <= 1e-5 result, no error.
+    spike = 1: the common case, the verify pass returns at once."""
+    import torch
+    nt, nr, nsc, npkt, hidden = 32, 4, 1024, 8, (256, 192)          # 4.2 M floats of Y: above the sampling threshold
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    Y, _ = mm.synth.make_packets(45, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    Y = Y.copy()
+    if spike > 1:
+        Y[3, 1, :, 50] *= spike            # tone 50: second cache line of its 1 KB group, never sampled
+    elif spike < 1:
+        mask = np.ones(nsc, bool)
+        mask[np.arange(nsc) % 128 < 16] = False
+        Y[:, :, :, mask] *= spike          # everything the sample does NOT read is tiny ...
+        Y[:, :, :, ~mask] *= 1e-9          # ... and what it reads is far smaller still: provisional scale far too high
+    with mm.Engine(nt, nr, nsc, hidden=hidden, precision="fp16x3") as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr, Hi = eng.estimate(torch.from_numpy(Y).cuda())       # poll_flags inside: a latched range error would raise
+        Hr, Hi = Hr.cpu().numpy(), Hi.cpu().numpy()
+        Hr2, Hi2 = eng.estimate(Y)                              # host path, chunked: same planes
+    _, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
+    assert rel_l2(ref_r, Hr) <= TOL_DNN and rel_l2(ref_i, Hi) <= TOL_DNN, (rel_l2(ref_r, Hr), rel_l2(ref_i, Hi))
+    assert rel_l2(ref_r, Hr2) <= TOL_DNN and rel_l2(ref_i, Hi2) <= TOL_DNN
+
+
 def test_mixed_amplitude_batch_per_packet_accuracy():
     """One batch holding packets 0, 40 and 60 dB apart (users at different path loss): every PACKET, not only the
     batch as a whole, stays within 1e-5 with the per-call automatic scale (no biases: the worst case)."""
