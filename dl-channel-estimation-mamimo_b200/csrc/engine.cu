@@ -18,6 +18,7 @@
 #include "lmmse.cuh"
 #include "ls.cuh"
 #include "ofdm.cuh"
+#include "svd.cuh"
 #include "tables.h"
 
 using namespace mm;
@@ -905,9 +906,12 @@ mamimo_status run_chunked(mamimo_engine* e, int64_t n_units, int64_t units_per_c
     if (hr) {
       CK(e, cudaMemcpyAsync(reinterpret_cast<char*>(hr) + u0 * h_unit_bytes, e->st_hr[b], n * h_unit_bytes,
                             cudaMemcpyDeviceToHost, e->s_d2h));
-      CK(e, cudaMemcpyAsync(reinterpret_cast<char*>(hi) + u0 * h_unit_bytes, e->st_hi[b], n * h_unit_bytes,
-                            cudaMemcpyDeviceToHost, e->s_d2h));
-      e->stats.d2h_bytes += 2 * n * h_unit_bytes;
+      e->stats.d2h_bytes += n * h_unit_bytes;
+      if (hi) {
+        CK(e, cudaMemcpyAsync(reinterpret_cast<char*>(hi) + u0 * h_unit_bytes, e->st_hi[b], n * h_unit_bytes,
+                              cudaMemcpyDeviceToHost, e->s_d2h));
+        e->stats.d2h_bytes += n * h_unit_bytes;
+      }
     }
     CK(e, cudaEventRecord(e->ev_out[b], e->s_d2h));
   }
@@ -1952,6 +1956,51 @@ mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo_ctype h_ty
     return check_flags(e, st);
   }
   return MAMIMO_OK;
+}
+
+// ---- next row: per-subcarrier SVD invariants of H-hat, omphybweights.m:169-176 -------------------
+mamimo_status mamimo_svd(mamimo_engine* e, const void* H, mamimo_ctype h_type, int64_t n_pkt, void* sigma, void* V1,
+                         mamimo_ctype out_type, mamimo_mem mem, void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (n_pkt < 0 || (n_pkt > 0 && (!H || !sigma))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if (e->cfg.n_rx > 8) return fail(e, MAMIMO_ERR_UNSUPPORTED, "mamimo_svd supports n_rx <= 8");
+  if ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(sigma) | reinterpret_cast<uintptr_t>(V1)) & 15)
+    return fail(e, MAMIMO_ERR_INVALID, "H, sigma and V1 must be 16-byte aligned");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const int nr = e->cfg.n_rx, nt = e->cfg.n_tx, nsc = e->cfg.n_sc;
+  const size_t hb = static_cast<size_t>(nr) * nt * nsc * (h_type == MAMIMO_C128 ? 16 : 8);
+  const size_t vb = static_cast<size_t>(nr) * nt * nsc * (out_type == MAMIMO_C128 ? 16 : 8);
+  const size_t sb = static_cast<size_t>(nr) * nsc * (out_type == MAMIMO_C128 ? 8 : 4);
+  auto stage = [&](int64_t n, const void* in0, const void*, void* v1, float* sg, float*, cudaStream_t st) {
+    SvdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = in0; a.sigma = sg; a.V1 = v1;
+    a.h_double = h_type == MAMIMO_C128; a.out_double = out_type == MAMIMO_C128;
+    a.n_tx = nt; a.n_sc = nsc;
+    const dim3 grid((nsc + 127) / 128, static_cast<unsigned>(n));
+    const dim3 grid_s((nsc + kSvdSmemThreads - 1) / kSvdSmemThreads, static_cast<unsigned>(n));
+    ProfScope ps(e, st, kClsStage);
+#define SVD_SMEM_CASE(NR)                                                                                              \
+  CK(e, cudaFuncSetAttribute(svd_gram_smem_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, svd_smem_bytes<NR>())); \
+  svd_gram_smem_kernel<NR><<<grid_s, kSvdSmemThreads, svd_smem_bytes<NR>(), st>>>(a);
+    switch (nr) {
+      case 1: svd_gram_kernel<1><<<grid, 128, 0, st>>>(a); break;
+      case 2: svd_gram_kernel<2><<<grid, 128, 0, st>>>(a); break;
+      case 3: svd_gram_kernel<3><<<grid, 128, 0, st>>>(a); break;
+      case 4: svd_gram_kernel<4><<<grid, 128, 0, st>>>(a); break;
+      case 5: { SVD_SMEM_CASE(5) } break;
+      case 6: { SVD_SMEM_CASE(6) } break;
+      case 7: { SVD_SMEM_CASE(7) } break;
+      default: { SVD_SMEM_CASE(8) } break;
+    }
+#undef SVD_SMEM_CASE
+    CK(e, cudaGetLastError());
+    e->stats.kernel_launches++;
+    return MAMIMO_OK;
+  };
+  // chunks of at most 65535 packets (grid.y); the host path additionally streams in host_chunk units
+  return run_chunked(e, n_pkt, std::min<int64_t>(e->max_pkts, 65535), H, hb, nullptr, 0, V1, vb, static_cast<float*>(sigma),
+                     nullptr, sb, mem, static_cast<cudaStream_t>(stream), stage);
 }
 
 mamimo_status mamimo_synchronize(mamimo_engine* e) {

@@ -370,6 +370,42 @@ class Engine:
               self._h)
         return out
 
+    # ------------------------------------------------------------------ per-subcarrier SVD
+    def svd(self, H, want_vectors=True, check_flags=True):
+        """Singular values and dominant right singular vectors of every per-tone [n_rx x n_tx] channel matrix
+        (pg/omphybweights.m:174-176: H = Hin.'; [~,~,v] = svd(H)).  H [n_pkt, n_rx, n_tx, n_sc] complex64/128 (numpy =
+        host, torch CUDA = device) -> sigma [n_pkt, n_rx, n_sc] (descending along axis 1) and V1 [n_pkt, n_rx, n_tx, n_sc]
+        with V1[p, r, :, k] = v_r of tone k (unique up to a phase; V1 V1^H is the projector onto the row space)."""
+        c = self.cfg
+        if tuple(H.shape[1:]) != (c.n_rx, c.n_tx, c.n_sc):
+            raise ValueError("H must be [n_pkt, n_rx=%d, n_tx=%d, n_sc=%d]" % (c.n_rx, c.n_tx, c.n_sc))
+        n_pkt = int(H.shape[0])
+        if _is_torch_cuda(H):
+            import torch
+            if H.dtype not in (torch.complex64, torch.complex128):
+                raise TypeError("H must be complex64 or complex128")
+            H = H.contiguous()
+            dbl = H.dtype == torch.complex128
+            sig = torch.empty((n_pkt, c.n_rx, c.n_sc), dtype=torch.float64 if dbl else torch.float32, device=H.device)
+            V = torch.empty_like(H) if want_vectors else None
+            t = _capi.C128 if dbl else _capi.C64
+            st = torch.cuda.current_stream(H.device).cuda_stream
+            check(lib.mamimo_svd(self._h, C.c_void_p(H.data_ptr()), t, n_pkt, C.c_void_p(sig.data_ptr()),
+                                 C.c_void_p(V.data_ptr()) if want_vectors else None, t, _capi.MEM_DEVICE, C.c_void_p(st)), self._h)
+            if check_flags:
+                self.poll_flags(st)
+            return (sig, V) if want_vectors else sig
+        H = np.ascontiguousarray(H)
+        if H.dtype not in (np.complex64, np.complex128):
+            raise TypeError("H must be complex64 or complex128")
+        dbl = H.dtype == np.complex128
+        t = _capi.C128 if dbl else _capi.C64
+        sig = np.empty((n_pkt, c.n_rx, c.n_sc), dtype=np.float64 if dbl else np.float32)
+        V = np.empty_like(H) if want_vectors else None
+        check(lib.mamimo_svd(self._h, _np_ptr(H), t, n_pkt, _np_ptr(sig), _np_ptr(V) if want_vectors else None, t,
+                             _capi.MEM_HOST, None), self._h)
+        return (sig, V) if want_vectors else sig
+
     def debug_counters(self, reset=True):
         """role counters of the CTA-pair FC kernel (mamimo_get_debug_counters; debug build + MAMIMO_FC_DEBUG=1)"""
         out = (C.c_uint64 * 8)()

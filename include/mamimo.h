@@ -239,6 +239,16 @@ MAMIMO_API mamimo_status mamimo_lmmse(mamimo_engine* e, const void* H_ls, mamimo
 /* tau_rms of LMMSE_ce.m:27-30 for h [n] (real, or complex interleaved when is_complex) */
 MAMIMO_API double mamimo_tau_rms(const double* h, int32_t n, int32_t is_complex);
 
+/* ---- next row: per-subcarrier SVD of H-hat, the first step of the hybrid-precoder consumer -------
+ * Replaces `H = Hin.'; [~,~,v] = svd(H); Fopt = v(:,1:Ns)` of pg/omphybweights.m:174-176 (per subcarrier, called from
+ * pg/BER_test_maMIMO_LTF.m:372) for every (packet, tone) of a batch, restricted to what does not depend on LAPACK's
+ * choice of basis: the n_rx singular values (descending) and the n_rx dominant right singular vectors of the
+ * [n_rx x n_tx] matrix H(i,j) = H-hat[pkt][i][j][k] (each vector unique up to a phase; V1 V1^H is unique).
+ * H complex [n_pkt][n_rx][n_tx][n_sc]; sigma real [n_pkt][n_rx][n_sc] (float for MAMIMO_C64 out_type, double for
+ * MAMIMO_C128); V1 complex [n_pkt][n_rx][n_tx][n_sc] = v_r[j] of tone k at [r][j][k], may be NULL.  n_rx <= 8. */
+MAMIMO_API mamimo_status mamimo_svd(mamimo_engine* e, const void* H, mamimo_ctype h_type, int64_t n_pkt, void* sigma,
+                                    void* V1, mamimo_ctype out_type, mamimo_mem mem, void* stream);
+
 /* Error reporting of DEVICE-buffer calls.  Every entry point taking mem == MAMIMO_MEM_DEVICE only enqueues work on
  * `stream` and returns; conditions its kernels detect (MAMIMO_ERR_RANGE, MAMIMO_ERR_TIMEOUT, LMMSE not-PD) are
  * latched in a device flag word and reported -- and cleared -- by the next mamimo_synchronize (waits for the whole

@@ -24,8 +24,10 @@ Pinning status (see DESIGN.md "Oracle"):
 * ``oracle.mlp`` (Keras FC graph) restates TensorFlow layer semantics that cannot run here (no TensorFlow / h5py):
   **parity unpinned** by execution of TensorFlow itself; the glue around it (``CSIPredictor.inference`` end to end
   with a numpy Keras stand-in) is pinned, and the layer arithmetic is anchored on BN-fold == unfused identities.
+* ``oracle.svd`` (first lines of omphybweights.m's getWeightsForSubcarrier) is PINNED on those lines executed by
+  ``mini_matlab`` (``tests/golden/ref_svd.npz``), through the basis-independent invariants only.
 * ``oracle.interp`` has no reference counterpart at all (the reference always
   uses Nps = 1): **parity unpinned**, defined here.
 """
 
-from . import tables, ls, mlp, postproc, interp, lmmse  # noqa: F401
+from . import tables, ls, mlp, postproc, interp, lmmse, svd  # noqa: F401

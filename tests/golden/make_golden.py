@@ -330,7 +330,39 @@ def run_ber_test_reader():
     return out
 
 
+# ---------------------------------------------------------------- 7. omphybweights.m: the per-subcarrier SVD lines
+def run_omp_svd_lines():
+    """getWeightsForSubcarrier's first statements (pg/omphybweights.m:174-176), literally:
+    H = Hin.'; [~,~,v] = svd(H); Fopt = v(:,1:Ns);  -- svd itself is LAPACK (numpy here, MATLAB there)."""
+    from mini_matlab import MatlabFile
+    src = open(os.path.join(REF, "packet_generation/phased_arr/omphybweights.m"), encoding="latin-1").read()
+    lines = src.splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.strip() == "H = Hin.';")
+    body = lines[i0:i0 + 3]
+    assert body[1].strip() == "[~,~,v] = svd(H);" and body[2].strip() == "Fopt = v(:,1:Ns);"
+    wrap = "function [Fopt, H] = topsvd(Hin, Ns)\n" + "\n".join(body) + "\nend\n"
+
+    def svd(A):
+        U, S, Vh = np.linalg.svd(np.asarray(A), full_matrices=True)
+        Sm = np.zeros(A.shape)
+        Sm[:len(S), :len(S)] = np.diag(S)
+        return U, Sm, Vh.conj().T
+
+    m = MatlabFile(wrap, externals={"svd": svd})
+    rng = np.random.default_rng(6706)
+    out = {}
+    for tag, (nt, nr, n) in {"a": (8, 2, 5), "b": (32, 4, 6), "c": (4, 4, 3)}.items():
+        Hin = rng.standard_normal((n, nt, nr)) + 1j * rng.standard_normal((n, nt, nr))      # n "subcarriers" of [Nt x Nr]
+        if tag == "b":
+            Hin[2] *= 1e-3                                                                   # amplitude spread
+            Hin[4, :, 3] = Hin[4, :, 2] * (0.5 - 0.2j)                                        # one rank-deficient matrix
+        F = np.stack([m.call("topsvd", [Hin[k], float(nt)], 1)[0] for k in range(n)])
+        out["Hin_" + tag], out["Fopt_" + tag] = Hin, F
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "ref_svd.npz"), **run_omp_svd_lines())
     np.savez_compressed(os.path.join(HERE, "ref_ber_test_reader.npz"), **run_ber_test_reader())
     np.savez_compressed(os.path.join(HERE, "ref_matlab_ls_lmmse.npz"), **run_matlab_hot_path())
     install_stub_tf(lambda path: None)
