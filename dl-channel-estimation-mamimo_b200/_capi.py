@@ -48,7 +48,7 @@ class Profile(C.Structure):
 SYMBOLS = [
     "mamimo_abi_version", "mamimo_status_string", "mamimo_last_error", "mamimo_config_init",
     "mamimo_vht_ltf256", "mamimo_carriers_locations", "mamimo_default_p", "mamimo_pair_row",
-    "mamimo_create", "mamimo_destroy", "mamimo_set_pilots", "mamimo_load_layer", "mamimo_finalize_weights",
+    "mamimo_create", "mamimo_destroy", "mamimo_set_pilots", "mamimo_set_pilots_f64", "mamimo_load_layer", "mamimo_finalize_weights",
     "mamimo_ls_estimate", "mamimo_estimate", "mamimo_estimate_stages", "mamimo_predict_planes", "mamimo_predict_time",
     "mamimo_synchronize", "mamimo_poll_flags", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end", "mamimo_get_debug_counters",
@@ -78,6 +78,7 @@ def _load():
         "mamimo_create": (i32, [C.POINTER(Config), C.POINTER(vp)]),
         "mamimo_destroy": (None, [vp]),
         "mamimo_set_pilots": (i32, [vp, vp, vp]),
+        "mamimo_set_pilots_f64": (i32, [vp, vp, vp]),
         "mamimo_load_layer": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "mamimo_finalize_weights": (i32, [vp]),
         "mamimo_ls_estimate": (i32, [vp, vp, i32, i32, i64, vp, i32, i32, vp]),

@@ -102,6 +102,9 @@ struct mamimo_engine {
   std::vector<float> hP;        // [n_tx][n_ltf] complex interleaved
   float2* dP = nullptr;
   float2* d_inv_den = nullptr;
+  std::vector<double> hPd;      // the same tables in double (mamimo_set_pilots_f64; FP64 LS of the MATLAB-facing surface)
+  double2* dPd = nullptr;
+  double2* d_inv_den_d = nullptr;
   HostLayer hl[2][MAMIMO_MAX_HIDDEN + 1];
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
@@ -1145,7 +1148,7 @@ void mamimo_destroy(mamimo_engine* e) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(e->gather_local[0]); fr(e->gather_local[1]);
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
-  fr(e->dP); fr(e->d_inv_den); fr(e->d_flags); fr(e->d_dyn); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->dP); fr(e->d_inv_den); fr(e->dPd); fr(e->d_inv_den_d); fr(e->d_flags); fr(e->d_dyn); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -1171,33 +1174,39 @@ void mamimo_destroy(mamimo_engine* e) {
   delete e;
 }
 
-mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P) {
-  if (!e) return MAMIMO_ERR_INVALID;
+namespace {
+// tables in double: x_pilot [n_pil] and P [n_tx][n_ltf], complex interleaved (either may be NULL = defaults)
+mamimo_status set_pilots_impl(mamimo_engine* e, const double* x_pilot, const double* P) {
   invalidate_graphs(e);
   CK(e, cudaSetDevice(e->cfg.device));
   const int nt = e->cfg.n_tx, nl = e->cfg.n_ltf;
-  e->hP.assign(static_cast<size_t>(2) * nt * nl, 0.f);
+  e->hPd.assign(static_cast<size_t>(2) * nt * nl, 0.0);
   if (P) {
-    memcpy(e->hP.data(), P, e->hP.size() * sizeof(float));
+    memcpy(e->hPd.data(), P, e->hPd.size() * sizeof(double));
   } else {
     if (nt == nl && (nt & (nt - 1)) == 0) {
       for (int j = 0; j < nt; ++j)
-        for (int n = 0; n < nl; ++n) e->hP[2 * (j * nl + n)] = (__builtin_popcount(j & n) & 1) ? -1.f : 1.f;
+        for (int n = 0; n < nl; ++n) e->hPd[2 * (j * nl + n)] = (__builtin_popcount(j & n) & 1) ? -1.0 : 1.0;
     } else if (nl == 1) {
-      for (int j = 0; j < nt; ++j) e->hP[2 * j] = 1.f;
+      for (int j = 0; j < nt; ++j) e->hPd[2 * j] = 1.0;
     } else {
       return fail(e, MAMIMO_ERR_INVALID, "no default P for this (n_tx, n_ltf): pass P explicitly");
     }
   }
+  e->hP.resize(e->hPd.size());
+  for (size_t i = 0; i < e->hPd.size(); ++i) e->hP[i] = static_cast<float>(e->hPd[i]);
   e->hadamard = is_sylvester(e->hP, nt, nl);
   std::vector<float> inv(static_cast<size_t>(2) * e->n_pil);
+  std::vector<double> invd(static_cast<size_t>(2) * e->n_pil);
   double inv_max = 0;
   for (int i = 0; i < e->n_pil; ++i) {
     const double xr = x_pilot ? x_pilot[2 * i] : 1.0, xi = x_pilot ? x_pilot[2 * i + 1] : 0.0;
     const double den = (xr * xr + xi * xi) * nl;
     if (den == 0.0) return fail(e, MAMIMO_ERR_INVALID, "pilot tone " + std::to_string(i) + " is zero");
-    inv[2 * i] = static_cast<float>(xr / den);          // 1/(nl*x) = conj(x)/(nl*|x|^2)
-    inv[2 * i + 1] = static_cast<float>(-xi / den);
+    invd[2 * i] = xr / den;                              // 1/(nl*x) = conj(x)/(nl*|x|^2)
+    invd[2 * i + 1] = -xi / den;
+    inv[2 * i] = static_cast<float>(invd[2 * i]);
+    inv[2 * i + 1] = static_cast<float>(invd[2 * i + 1]);
     inv_max = std::max(inv_max, std::sqrt(xr * xr + xi * xi) / den);
   }
   {
@@ -1206,17 +1215,35 @@ mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const fl
     double prow = 0;
     for (int j = 0; j < nt; ++j) {
       double r = 0;
-      for (int n = 0; n < nl; ++n) r += std::hypot(e->hP[2 * (j * nl + n)], e->hP[2 * (j * nl + n) + 1]);
+      for (int n = 0; n < nl; ++n) r += std::hypot(e->hPd[2 * (j * nl + n)], e->hPd[2 * (j * nl + n) + 1]);
       prow = std::max(prow, r);
     }
     e->ls_gain = static_cast<float>(1.41421357 * prow * inv_max * (e->cfg.n_ps > 1 ? 5.0 : 1.0) * (1.0 + 1e-5));
   }
   if (!e->dP) CK(e, cudaMalloc(&e->dP, e->hP.size() * sizeof(float)));
   if (!e->d_inv_den) CK(e, cudaMalloc(&e->d_inv_den, inv.size() * sizeof(float)));
+  if (!e->dPd) CK(e, cudaMalloc(&e->dPd, e->hPd.size() * sizeof(double)));
+  if (!e->d_inv_den_d) CK(e, cudaMalloc(&e->d_inv_den_d, invd.size() * sizeof(double)));
   CK(e, cudaMemcpy(e->dP, e->hP.data(), e->hP.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(e, cudaMemcpy(e->d_inv_den, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(e, cudaMemcpy(e->dPd, e->hPd.data(), e->hPd.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(e, cudaMemcpy(e->d_inv_den_d, invd.data(), invd.size() * sizeof(double), cudaMemcpyHostToDevice));
   if (e->finalized) return rebuild_mode_a_table(e);       // mode A: the P-row term of the first layer depends on P
   return MAMIMO_OK;
+}
+}  // namespace
+
+mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  std::vector<double> xd, pd;
+  if (x_pilot) xd.assign(x_pilot, x_pilot + static_cast<size_t>(2) * e->n_pil);
+  if (P) pd.assign(P, P + static_cast<size_t>(2) * e->cfg.n_tx * e->cfg.n_ltf);
+  return set_pilots_impl(e, x_pilot ? xd.data() : nullptr, P ? pd.data() : nullptr);
+}
+
+mamimo_status mamimo_set_pilots_f64(mamimo_engine* e, const double* x_pilot, const double* P) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  return set_pilots_impl(e, x_pilot, P);
 }
 
 mamimo_status mamimo_load_layer(mamimo_engine* e, int32_t net, int32_t layer, const float* W, const float* b,
@@ -1313,7 +1340,26 @@ mamimo_status mamimo_ls_estimate(mamimo_engine* e, const void* Y, mamimo_ctype y
   CK(e, cudaSetDevice(e->cfg.device));
   const size_t yb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_ltf * e->cfg.n_sc * (y_type == MAMIMO_C128 ? 16 : 8);
   const size_t hb = static_cast<size_t>(e->cfg.n_rx) * e->cfg.n_tx * e->cfg.n_sc * (h_type == MAMIMO_C128 ? 16 : 8);
+  const bool f64 = y_type == MAMIMO_C128 && h_type == MAMIMO_C128 && e->dPd && getenv("MAMIMO_LS_F64_OFF") == nullptr;
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float*, float*, cudaStream_t st) {
+    if (f64) {      // complex double in and out: double arithmetic, as helperMIMOChannelEstimate.m:33-36 computes it
+      LsF64Args a;
+      a.Y = static_cast<const double2*>(in0); a.P = e->dPd; a.inv_den = e->d_inv_den_d; a.H = static_cast<double2*>(hls);
+      a.n_rx = e->cfg.n_rx; a.n_tx = e->cfg.n_tx; a.n_ltf = e->cfg.n_ltf; a.n_sc = e->cfg.n_sc; a.n_ps = e->cfg.n_ps;
+      a.n_pil = e->n_pil;
+      const long long gy = static_cast<long long>(n) * a.n_rx * a.n_tx;
+      for (long long y0 = 0; y0 < gy; y0 += 65535 / a.n_tx * a.n_tx) {      // grid.y limit; whole (pkt, rx) groups per launch
+        const long long ny = std::min<long long>(65535 / a.n_tx * a.n_tx, gy - y0);
+        LsF64Args b = a;
+        b.Y = a.Y + (y0 / a.n_tx) * a.n_ltf * static_cast<size_t>(a.n_sc);
+        b.H = a.H + y0 * static_cast<size_t>(a.n_sc);
+        ProfScope ps(e, st, kClsLs);
+        ls_f64_kernel<<<dim3((a.n_sc + 127) / 128, static_cast<unsigned>(ny)), 128, 0, st>>>(b);
+        CK(e, cudaGetLastError());
+        e->stats.kernel_launches++;
+      }
+      return MAMIMO_OK;
+    }
     return DISPATCH_S(e, (run_ls<S>(e, in0, y_type == MAMIMO_C128, static_cast<int>(n), hls, h_type == MAMIMO_C128, false, st)));
   };
   return run_chunked(e, n_pkt, e->max_pkts, Y, yb, nullptr, 0, H_ls, hb, nullptr, nullptr, 0, y_mem,
@@ -1657,6 +1703,7 @@ mamimo_status mamimo_set_ofdm(mamimo_engine* e, int32_t fft_len, int32_t cp_len,
   if (!e) return MAMIMO_ERR_INVALID;
   if (fft_len < 2 || fft_len > 4096 || (fft_len & (fft_len - 1))) return fail(e, MAMIMO_ERR_INVALID, "fft_len must be a power of two in [2, 4096]");
   if (cp_len < 0 || sym_offset < 0 || sym_offset > cp_len) return fail(e, MAMIMO_ERR_INVALID, "need 0 <= sym_offset <= cp_len");
+  if (cp_len > fft_len) return fail(e, MAMIMO_ERR_INVALID, "cyclic prefix longer than the FFT (the window start would fall before the symbol)");
   if (!carriers) return fail(e, MAMIMO_ERR_INVALID, "carriers is NULL");
   if (e->cfg.n_sc > fft_len) return fail(e, MAMIMO_ERR_INVALID, "n_sc exceeds fft_len");
   CK(e, cudaSetDevice(e->cfg.device));

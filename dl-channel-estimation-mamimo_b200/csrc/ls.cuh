@@ -506,6 +506,53 @@ __global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_c
   if (a.planes[0]) { publish_amax<S>(a.dyn, 0, 0, amx[0]); publish_amax<S>(a.dyn, 1, 0, amx[1]); }
 }
 
+// ---- FP64 LS for the MATLAB-facing surface (complex128 in AND out, no operand planes) ----------------------------
+// helperMIMOChannelEstimate.m computes hD in double; a caller that hands over complex double and asks for complex double
+// back gets double arithmetic end to end (the FP32 kernels above would return FP32-grade values in a double container).
+// One thread per output element (pkt, rx, tx, k): despread of its pilot tone(s) against row tx of P in FP64 -- O(n_ltf)
+// per output, the n_tx threads of a tone re-read the same Y values from L1/L2.  Not the hot path (that one ends in FP32
+// operand planes anyway); HBM traffic is the algorithmic 2 x 16 B per element.
+struct LsF64Args {
+  const double2* Y;        // [n_pkt][n_rx][n_ltf][n_sc]
+  const double2* P;        // [n_tx][n_ltf]
+  const double2* inv_den;  // [n_pil]
+  double2* H;              // [n_pkt][n_rx][n_tx][n_sc]
+  int n_rx, n_tx, n_ltf, n_sc, n_ps, n_pil;
+};
+
+__device__ __forceinline__ double2 ls_f64_despread(const LsF64Args& a, const double2* y_slab, int j, int pil) {
+  const int k = pil * a.n_ps;
+  double ax = 0.0, ay = 0.0;
+  for (int n = 0; n < a.n_ltf; ++n) {
+    const double2 y = __ldg(y_slab + static_cast<size_t>(n) * a.n_sc + k);
+    const double2 p = __ldg(a.P + j * a.n_ltf + n);                         // y * conj(p)
+    ax = fma(y.x, p.x, fma(y.y, p.y, ax));
+    ay = fma(y.y, p.x, fma(-y.x, p.y, ay));
+  }
+  const double2 d = __ldg(a.inv_den + pil);
+  return make_double2(ax * d.x - ay * d.y, ax * d.y + ay * d.x);
+}
+
+__global__ void __launch_bounds__(128) ls_f64_kernel(const LsF64Args a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.n_sc) return;
+  const size_t prx = blockIdx.y / a.n_tx;                                   // pkt * n_rx + rx
+  const int j = blockIdx.y % a.n_tx;
+  const double2* y_slab = a.Y + prx * a.n_ltf * static_cast<size_t>(a.n_sc);
+  double2 h;
+  if (a.n_ps == 1) {
+    h = ls_f64_despread(a, y_slab, j, k);
+  } else if (a.n_pil == 1) {
+    h = ls_f64_despread(a, y_slab, j, 0);
+  } else {
+    const int seg = min(k / a.n_ps, a.n_pil - 2);
+    const double w = static_cast<double>(k - seg * a.n_ps) / a.n_ps;
+    const double2 h0 = ls_f64_despread(a, y_slab, j, seg), h1 = ls_f64_despread(a, y_slab, j, seg + 1);
+    h = make_double2(h0.x + w * (h1.x - h0.x), h0.y + w * (h1.y - h0.y));
+  }
+  a.H[(prx * a.n_tx + j) * static_cast<size_t>(a.n_sc) + k] = h;
+}
+
 // ---- mode B: caller planes float32 [rows][d_in] -> operand planes (inference.py:29-30) ----
 template <int S>
 __global__ void stage_planes_kernel(const float* __restrict__ X, void* planes, int64_t rows, int d_in,

@@ -100,15 +100,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       mexErrMsgIdAndTxt("mamimo:usage", "pilots needs real double ltf_o and P");
     const size_t np = mxGetNumberOfElements(prhs[1]), nP = mxGetNumberOfElements(prhs[2]);
     if (nP != (size_t)g_cfg.n_tx * g_cfg.n_ltf) mexErrMsgIdAndTxt("mamimo:size", "P must be [numSTS x nltf]");
-    static float xp[2 * 65536], Pm[2 * 64 * 64];
+    static double xp[2 * 65536], Pm[2 * 64 * 64];      // double tables: 'ls' on complex double runs in FP64 like MATLAB
     if (np > 65536) mexErrMsgIdAndTxt("mamimo:size", "too many pilot tones");
-    for (size_t i = 0; i < np; ++i) { xp[2 * i] = (float)mxGetDoubles(prhs[1])[i]; xp[2 * i + 1] = 0.f; }
+    for (size_t i = 0; i < np; ++i) { xp[2 * i] = mxGetDoubles(prhs[1])[i]; xp[2 * i + 1] = 0.0; }
     for (int j = 0; j < g_cfg.n_tx; ++j)            // MATLAB column-major P(j,n) -> row-major [tx][ltf]
       for (int n = 0; n < g_cfg.n_ltf; ++n) {
-        Pm[2 * (j * g_cfg.n_ltf + n)] = (float)mxGetDoubles(prhs[2])[n * g_cfg.n_tx + j];
-        Pm[2 * (j * g_cfg.n_ltf + n) + 1] = 0.f;
+        Pm[2 * (j * g_cfg.n_ltf + n)] = mxGetDoubles(prhs[2])[n * g_cfg.n_tx + j];
+        Pm[2 * (j * g_cfg.n_ltf + n) + 1] = 0.0;
       }
-    fail(mamimo_set_pilots(g_engine, xp, Pm));
+    fail(mamimo_set_pilots_f64(g_engine, xp, Pm));
   } else if (!strcmp(cmd, "load")) {
     need_engine();
     if (nrhs != 5 && nrhs != 9) mexErrMsgIdAndTxt("mamimo:usage", "load(net, layer, W, b [, gamma, beta, mean, var])");

@@ -112,14 +112,15 @@ class Engine:
     # ------------------------------------------------------------------ tables / weights
     def set_pilots(self, x_pilot=None, P=None):
         """x_pilot [n_pilots] (ltf(ind), helperMIMOChannelEstimate.m:27) and P [n_tx, n_ltf] (helperGetP, :13)."""
-        xp = None if x_pilot is None else np.ascontiguousarray(np.asarray(x_pilot, dtype=np.complex64))
-        Pm = None if P is None else np.ascontiguousarray(np.asarray(P, dtype=np.complex64))
+        xp = None if x_pilot is None else np.ascontiguousarray(np.asarray(x_pilot, dtype=np.complex128))
+        Pm = None if P is None else np.ascontiguousarray(np.asarray(P, dtype=np.complex128))
         if Pm is not None and Pm.shape != (self.cfg.n_tx, self.cfg.n_ltf):
             raise ValueError("P must be [n_tx, n_ltf]")
         n_pil = (self.cfg.n_sc + self.cfg.n_ps - 1) // self.cfg.n_ps
         if xp is not None and xp.shape != (n_pil,):
             raise ValueError("x_pilot must have %d entries" % n_pil)
-        check(lib.mamimo_set_pilots(self._h, None if xp is None else _np_ptr(xp), None if Pm is None else _np_ptr(Pm)),
+        # double-precision tables: complex128 LS calls compute in FP64 end to end, everything else rounds them to FP32
+        check(lib.mamimo_set_pilots_f64(self._h, None if xp is None else _np_ptr(xp), None if Pm is None else _np_ptr(Pm)),
               self._h)
 
     def load_weights(self, nets):
@@ -494,7 +495,9 @@ def helperMIMOChannelEstimate(rxData, prm, Nps=1, tau=None, SNR=None, isMMSE=Fal
     Same argument meaning as pg/helperMIMOChannelEstimate.m:1.  rxData complex [Nsc, nltf, Nr]
     (MATLAB logical shape) or [Nsc, nltf, Nr, Npkt] for a batch hoisted out of the packet loop;
     prm needs 'numSTS' and 'CarriersLocations' (1-based, :9,26).  Returns hD [Nsc, numSTS, Nr(, Npkt)]
-    complex128, P, ltf_o = ltf(ind) (:29) and hDmmse (zeros unless isMMSE, as in the reference :32).  With
+    complex128 -- computed in FP64 on the device like MATLAB's (rxData is handed over as complex128 and the engine's
+    complex128-in / complex128-out LS runs in double) --, P, ltf_o = ltf(ind) (:29) and hDmmse (zeros unless isMMSE,
+    as in the reference :32).  With
     isMMSE, tau is LMMSE_ce's `h` vector (one per call, or a list of Npkt vectors for a batch) and SNR is SNR(i)
     in dB, [Nr] or [Nr, Npkt] (:37-39).
     """
@@ -527,13 +530,20 @@ def helperMIMOChannelEstimate(rxData, prm, Nps=1, tau=None, SNR=None, isMMSE=Fal
     H = eng.ls_estimate(Y)                                   # [Npkt, Nr, Nt, Nsc]
     hD = np.transpose(H, (3, 2, 1, 0))
     if isMMSE:
-        if Nps != 1 and Nps != eng.cfg.n_ps:
-            raise ValueError("Nps=%d: the cached LS engine was built for pilot spacing %d" % (Nps, eng.cfg.n_ps))
+        # the reference applies Nps inside LMMSE_ce only (:38; LS itself always sees every tone): a second engine
+        # carries the pilot spacing of the smoother
+        if int(Nps) != 1:
+            lkey = (num_sts, nrx, nsc, device, "lmmse", int(Nps))
+            leng = _ENGINE_CACHE.get(lkey)
+            if leng is None:
+                leng = _ENGINE_CACHE[lkey] = Engine(num_sts, nrx, nsc, n_ps=int(Nps), mlp=False, device=device)
+        else:
+            leng = eng
         taus = tau if (isinstance(tau, (list, tuple)) and len(tau) == npkt and np.ndim(tau[0]) > 0) else [tau] * npkt
         t_rms = np.array([tau_rms(t) for t in taus])
         snr = np.asarray(SNR, dtype=np.float64)
         snr = np.broadcast_to(snr.reshape(nrx, -1).T, (npkt, nrx))     # [Nr] or [Nr, Npkt] -> [Npkt, Nr]
-        hM = np.transpose(eng.lmmse(H, t_rms, snr), (3, 2, 1, 0))
+        hM = np.transpose(leng.lmmse(H, t_rms, snr), (3, 2, 1, 0))
     else:
         hM = np.zeros_like(hD)
     if squeeze:

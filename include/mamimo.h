@@ -143,6 +143,10 @@ MAMIMO_API void mamimo_destroy(mamimo_engine* e);
  * mapping matrix P [n_tx][n_ltf] (complex64 interleaved; NULL = default_p).  Replaces ltf(ind) and
  * helperGetP in pg/helperMIMOChannelEstimate.m:13,27. */
 MAMIMO_API mamimo_status mamimo_set_pilots(mamimo_engine* e, const float* x_pilot, const float* P);
+/* The same tables in double precision (complex128 interleaved).  mamimo_ls_estimate with complex128 Y AND complex128
+ * H_ls then runs the despread in FP64 end to end, as MATLAB does (hD matches helperMIMOChannelEstimate.m to ~1e-15);
+ * every other combination computes in FP32 (the hot path ends in FP32 operand planes). */
+MAMIMO_API mamimo_status mamimo_set_pilots_f64(mamimo_engine* e, const double* x_pilot, const double* P);
 
 /* One Dense layer of net (0 = 'real', 1 = 'imag'); layer in [0, n_hidden].  W is the Keras kernel
  * [in][out] row-major, b [out]; BN vectors [out] (all NULL when the layer has no BatchNormalization;

@@ -69,6 +69,49 @@ def test_ls_dense_p_parity(nt):
     assert rel_l2(oracle_ls(Y, P, x), H) <= TOL_LS
 
 
+@pytest.mark.parametrize("nt,nr,nsc,npkt,nps", [(32, 4, 234, 3, 1), (8, 3, 234, 2, 1), (1, 2, 234, 2, 1), (6, 2, 96, 2, 1),
+                                                (8, 2, 100, 2, 3), (64, 8, 512, 2, 1)])
+def test_ls_complex128_in_and_out_runs_in_double(nt, nr, nsc, npkt, nps):
+    """The MATLAB-facing surface: complex double in, complex double out (pg/helperMIMOChannelEstimate.m:31-36 computes hD in
+    double) -> FP64 despread on the device, 1e-13 against the FP64 oracle instead of the FP32 kernels' 1e-7; also with a
+    complex (DFT) P, which the FP32 tables would have rounded, and with comb pilots."""
+    rng = np.random.default_rng(7)
+    P = np.fft.fft(np.eye(nt)) if nt == 6 else tables.sylvester_hadamard(nt)
+    xp = mm.synth.make_pilots(nsc, nps)
+    x_full = np.ones(nsc)
+    x_full[::nps] = xp
+    Y, _ = mm.synth.make_packets(18, npkt, nt, nr, nsc, snr_db=10.0, P=P, x_tones=x_full, dtype=np.complex128)
+    Y = Y * (1 + 1e-9 * rng.standard_normal(Y.shape))            # bits below float precision that FP32 would drop
+    with mm.Engine(nt, nr, nsc, n_ps=nps, mlp=False) as eng:
+        eng.set_pilots(xp, P)
+        H = eng.ls_estimate(Y)
+        H32 = eng.ls_estimate(Y.astype(np.complex64))
+    ref = oracle_ls(Y, P, xp, nps)
+    assert H.dtype == np.complex128 and rel_l2(ref, H) <= 1e-13
+    assert 1e-9 < rel_l2(ref, H32) <= TOL_LS                      # the FP32 route really is a different, FP32-grade path
+
+
+def test_helper_dropin_matches_matlab_golden_in_double_and_passes_nps_to_the_smoother(golden_dir):
+    """helperMIMOChannelEstimate drop-in on the vectors produced by the unmodified .m files: hD to 1e-12 (FP64 on the
+    device), hDmmse to 1e-9; Nps != 1 goes to LMMSE_ce only (:38) while LS still sees every tone."""
+    from oracle import lmmse as o_lmmse
+    g = np.load(os.path.join(golden_dir, "ref_matlab_ls_lmmse.npz"))
+    for case in ("A", "C"):
+        rx, P = g["rx_" + case], g["P_" + case]
+        prm = {"numSTS": P.shape[0], "CarriersLocations": g["carriers"]}
+        hD, Pm, ltf_o, hM = mm.helperMIMOChannelEstimate(rx, prm, 1, g["tau_" + case].ravel(), g["snr_" + case].ravel(), True, P=P)
+        assert rel_l2(g["hD_" + case], hD) <= 1e-12 and np.array_equal(ltf_o, g["ltf_o_" + case])
+        if g["hDmmse_" + case].any():                           # case C was generated with isMMSE = false (zeros, :32)
+            assert rel_l2(g["hDmmse_" + case], hM) <= 1e-9
+    rx, P = g["rx_A"], g["P_A"]
+    prm = {"numSTS": P.shape[0], "CarriersLocations": g["carriers"]}
+    hD2, _, _, hM2 = mm.helperMIMOChannelEstimate(rx, prm, 2, g["tau_A"].ravel(), g["snr_A"].ravel(), True, P=P)
+    assert rel_l2(g["hD_A"], hD2) <= 1e-12                      # LS is untouched by Nps
+    H = np.transpose(hD2, (2, 1, 0))[None]
+    want = o_lmmse.lmmse_batched(H, o_lmmse.tau_rms(g["tau_A"].ravel()), g["snr_A"].reshape(1, -1), n_ps=2)
+    assert rel_l2(np.transpose(want[0], (2, 1, 0)), hM2) <= 1e-9
+
+
 def test_ls_noise_free_round_trip_full_size():
     """Config-2 shape: Y = x * H P  =>  LS returns H, here at 40 packets x 32x4x1024."""
     nt, nr, nsc, npkt = 32, 4, 1024, 40

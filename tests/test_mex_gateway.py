@@ -66,7 +66,7 @@ def test_gateway_ls_and_lmmse_reproduce_the_matlab_golden(mex, golden_dir, case)
     mex.call("pilots", ltf_o, P)
     hD = mex.call("ls", rx, nlhs=1)
     assert hD.shape == g["hD_" + case].shape and hD.dtype == np.complex128
-    assert rel_l2(g["hD_" + case], hD) <= 1e-6
+    assert rel_l2(g["hD_" + case], hD) <= 1e-12                  # complex double through 'ls': FP64 on the device
     has_mmse = bool(g["hDmmse_" + case].any())            # case B ran with isMMSE = false: hDmmse stays zeros (:32)
     hM = mex.call("lmmse", g["hD_" + case], g["tau_" + case], g["snr_" + case], nlhs=1)
     assert hM.shape == hD.shape and np.isfinite(hM).all()
