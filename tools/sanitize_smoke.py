@@ -82,4 +82,50 @@ with mm.Engine(32, 2, 128, hidden=(128, 64), precision="fp16x3") as eng:
     st.synchronize()
     assert eng.stats()["graph_launches"] == 2 and torch.isfinite(Hr).all()
     print("ok graph replay")
+# round 2: range bookkeeping (amax pre-pass, sampled + exact; provisional / verify / repair passes of the LS kernel),
+# pipelined fused all-gather (sub-batches with row offsets, both variants), FP64 LS, per-subcarrier SVD (registers and
+# shared-memory kernels), modes A / B with the automatic scale
+Yb, _ = mm.synth.make_packets(4, 8, 32, 4, 1024, snr_db=10.0, x_tones=mm.synth.make_pilots(1024))
+Yb = Yb.copy()
+Yb[2, 1, :, 50] *= 3e4                                          # unsampled spike: forces the repair pass
+netsb = mm.synth.make_nets(1024, (128,), 1024)
+for mode in ("fused", "ce"):
+    os.environ["MAMIMO_GATHER_MODE"], os.environ["MAMIMO_GATHER_SUB"], os.environ["MAMIMO_GATHER_SMS"] = mode, "3", "36"
+    with mm.Engine(32, 4, 1024, hidden=(128,), precision="fp16x3") as eng:
+        eng.set_pilots(mm.synth.make_pilots(1024), None)
+        eng.load_weights(netsb)
+        hr, hi = eng.estimate(Yb)
+        assert np.isfinite(hr).all()
+        eng.gather_create(1, 0, 8)
+        eng.gather_connect([eng._gather[3]], [eng._gather[4]])
+        Yd = torch.from_numpy(Yb).cuda()
+        eng.estimate_stages_raw(15, Yd.data_ptr(), 0, 8, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        gr, gi = eng.gather_planes()
+        assert np.allclose(gr.cpu().numpy(), hr, rtol=0, atol=1e-4 * np.abs(hr).max())
+    print("ok pipelined gather", mode)
+for k in ("MAMIMO_GATHER_MODE", "MAMIMO_GATHER_SUB", "MAMIMO_GATHER_SMS"):
+    os.environ.pop(k)
+with mm.Engine(6, 2, 100, n_ps=3, mlp=False) as eng:
+    eng.set_pilots(mm.synth.make_pilots(100, 3), np.fft.fft(np.eye(6)))
+    Yq = (np.random.default_rng(0).standard_normal((2, 2, 6, 100)) + 0j).astype(np.complex128)
+    assert np.isfinite(eng.ls_estimate(Yq)).all()
+    print("ok FP64 LS")
+for nt3, nr3 in ((8, 2), (32, 4), (16, 8)):
+    with mm.Engine(nt3, nr3, 70, mlp=False) as eng:
+        Hq = (np.random.default_rng(5).standard_normal((3, nr3, nt3, 70)) + 1j).astype(np.complex64)
+        sg, v1 = eng.svd(Hq)
+        assert np.isfinite(sg).all() and np.isfinite(v1).all()
+    print("ok svd", nt3, nr3)
+rng = np.random.default_rng(6)
+with mm.Engine(1, 1, 1, n_ltf=1, hidden=(64,), d_in=96, d_out=40, input_mode="planes", precision="fp16x3") as eng:
+    eng.load_weights(mm.synth.make_nets(96, (64,), 40))
+    a, b = eng.predict_planes(rng.standard_normal((70, 96)).astype(np.float32) * 1e-3, rng.standard_normal((70, 96)).astype(np.float32))
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+with mm.Engine(8, 2, 8, hidden=(64, 32), d_in=160 + 8, d_out=40, input_mode="time_p", len_ltf=160, precision="fp16x3") as eng:
+    eng.set_pilots(None, mm.synth.sylvester(8))
+    eng.load_weights(mm.synth.make_nets(168, (64, 32), 40))
+    a, b = eng.predict_time(rng.standard_normal((3, 2, 160)), rng.standard_normal((3, 2, 160)))
+    assert np.isfinite(a).all()
+print("ok modes A/B auto scale")
 print("sanitize smoke done")
