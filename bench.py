@@ -364,6 +364,27 @@ def run_ours(args):
     value = world * npkt / (ms_step * 1e-3)
     eng.poll_flags(stream.cuda_stream)
 
+    # ---- the same step back to back for >= args.sustain seconds: the board settles under its power cap (value above is
+    # what K steps after idle deliver; this is what a long-running job gets)
+    value_sustained = None
+    if args.sustain > 0:
+        barrier()
+        n_sus = 0
+        t_end = time.perf_counter() + args.sustain
+        ev0.record(stream)
+        while time.perf_counter() < t_end:
+            for _ in range(10):
+                step_device()
+            n_sus += 10
+            stream.synchronize()
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / n_sus], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_sustained = {"value": world * npkt / (float(t.item()) * 1e-3), "unit": "packets/s", "seconds": args.sustain,
+                           "steps": n_sus, "ms_per_step": float(t.item())}
+
     # ---- the same K steps again with every kernel bracketed by CUDA events on its stream (live per-kernel-class
     # profile for the rooflines; plain launches on ONE stream, because events inside a replayed graph cannot be read
     # back and brackets on two interleaved streams would overlap).  One second of idle first: back to back, the second
@@ -535,6 +556,8 @@ def run_ours(args):
             "pair_estimates_per_s": value * NT * NR, "us_per_packet": 1e6 / value,
             "ms_per_step_profiled": ms_prof_step,
         }
+        if value_sustained is not None:
+            line["value_sustained"] = value_sustained
         if value_compute_only is not None:
             line["value_compute_only"] = value_compute_only
         if gather_check is not None:
@@ -572,6 +595,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer region")
     ap.add_argument("--e2e-pkts", type=int, default=0, help="packets per end-to-end step (default: the batch, c4: 250)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison after the timed regions")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for value_sustained (0 = skip)")
     ap.add_argument("--timeline", default="", help="write rank 0's per-launch timeline of the profiled region to this CSV")
     args = ap.parse_args()
     global NT, NR, NSC, WORKLOAD, METRIC, MLP_FLOP_PER_PKT, LS_BYTES_PER_PKT, SNR_LEVELS

@@ -94,7 +94,7 @@ typedef struct {
                                does not depend on the amplitude of Y.  != 0 pins 2^act_scale_log2 for all levels (no
                                amax pre-pass); overflow AND underflow of the fp16 window then raise MAMIMO_ERR_RANGE */
   int32_t kb_per_chunk;     /* FC: k-blocks accumulated in the tensor core between FP32 register drains; 0 = default (4) */
-  int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default */
+  int32_t host_chunk_pkts;  /* packets (rows in mode B) per H2D/compute/D2H pipeline chunk for HOST buffers; 0 = default (~2K rows) */
   int32_t fc_single_cta;    /* 1 = use the 1-CTA FC kernel instead of the CTA-pair (cta_group::2) kernel */
   int32_t fc_sm_reserve;    /* SMs the persistent FC kernels leave free (room for a concurrent NCCL all-gather) */
   int32_t reserved[3];
