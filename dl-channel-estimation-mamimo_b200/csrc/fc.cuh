@@ -170,14 +170,21 @@ __device__ __forceinline__ void fc_epilogue_chunk(const FcArgs& a, const FcScale
     for (int q = 0; q < Sch::kPlanes; ++q) {
       E* dst = reinterpret_cast<E*>(a.out_planes) +
                (static_cast<size_t>(q) * a.out_plane_rows + a.row_off + row) * a.out_kpad + n0;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      // plane rows are kpad * sizeof(E) apart (a multiple of 128 B) and n0 is a multiple of 32 columns: 32-byte aligned
 #pragma unroll
-      for (int i = 0; i < kWords / 4; ++i)
-        d4[i] = make_uint4(pk[q][4 * i], pk[q][4 * i + 1], pk[q][4 * i + 2], pk[q][4 * i + 3]);
+      for (int i = 0; i < kWords / 8; ++i)
+        st_global_v8(reinterpret_cast<uint32_t*>(dst) + 8 * i, pk[q][8 * i], pk[q][8 * i + 1], pk[q][8 * i + 2],
+                     pk[q][8 * i + 3], pk[q][8 * i + 4], pk[q][8 * i + 5], pk[q][8 * i + 6], pk[q][8 * i + 7]);
     }
   } else {
     float* dst = a.out_f32 + static_cast<size_t>(row) * a.out_ld + n0;
-    if (n0 + 32 <= a.N && (a.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) {
+    if (n0 + 32 <= a.N && (a.out_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_global_v8(dst + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
+                     __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
+                     __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+    } else if (n0 + 32 <= a.N && (a.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);

@@ -29,6 +29,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// 32-byte global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane and instruction.  The FC epilogue
+// writes row-per-lane (lanes 2 KB apart), so every store instruction touches 32 sectors whatever its width: 256-bit
+// stores halve the instruction and sector-transaction count of 128-bit ones.  Address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
