@@ -1694,8 +1694,8 @@ mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, 
       CK(e, cudaStreamCreateWithFlags(&e->s_copy[p], cudaStreamNonBlocking));
       CK(e, cudaEventCreateWithFlags(&e->ev_copy[p], cudaEventDisableTiming));
     }
-  e->gather_sub = world >= 5 ? 6 : (world >= 3 ? 8 : 1);
-  e->gather_growth = world >= 5 ? 1.8 : 1.2;
+  e->gather_sub = world >= 3 ? 6 : 1;
+  e->gather_growth = world >= 5 ? 1.8 : 1.35;     // r2w/r2x sweeps (4 GPUs): 6 sub-batches x 1.35 = 3.17 ms, one shot 3.27 ms
   if (const char* env = getenv("MAMIMO_GATHER_SUB")) e->gather_sub = std::max(1, std::min(atoi(env), kDynSlotsMax));
   if (const char* env = getenv("MAMIMO_GATHER_GROWTH")) e->gather_growth = std::max(1.0, std::min(atof(env), 4.0));
   return MAMIMO_OK;
