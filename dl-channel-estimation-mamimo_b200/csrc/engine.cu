@@ -80,6 +80,9 @@ struct mamimo_engine {
   bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
   int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
   int ls_tile = 64;             // tones per CTA of the split LS kernel (MAMIMO_LS_TILE=128: experiment)
+  int ls_tile64 = 64;           // tones per tile of the TMA-fed LS kernel at 64 antennas.  MAMIMO_LS_TILE64=32 (16 KB stages,
+                                // 6 CTAs/SM instead of 3) measured SLOWER: 4.72 vs 4.93 TB/s at 64x8x2048 (r2G) -- the 256-byte
+                                // row segments cost more than the occupancy gives; kept as an experiment knob
   bool ls_split = true;         // LS: FWHT split over threads for 32/64 antennas (MAMIMO_LS_SPLIT=0 disables)
   unsigned long long* d_dbg = nullptr;   // MAMIMO_FC_DEBUG=1: role wait-cycle counters of the pair kernel
   int l2_prefetch = 0;             // measured slower (426 vs 442 TFLOP/s): kept as an experiment knob (MAMIMO_L2_PREFETCH)
@@ -385,30 +388,31 @@ mamimo_status launch_ls_split(mamimo_engine* e, const LsArgs& a, cudaStream_t st
 }
 
 // TMA-fed persistent LS kernel: per-call tensor map over Y viewed as float32 [n_pkt*n_rx*n_ltf][2*n_sc]
-template <int S, int NLTF, int STAGES, int NPS>
+template <int S, int NLTF, int STAGES, int NPS, int T = 64>
 mamimo_status launch_ls_tma(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   CUtensorMap map;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2) * a.n_sc, static_cast<cuuint64_t>(a.n_pkt) * a.n_rx * a.n_ltf};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.n_sc) * 8};
-  const cuuint32_t box[2] = {2u * ls_tma_row_tones<NPS>(), static_cast<cuuint32_t>(NLTF)};
+  const cuuint32_t box[2] = {2u * ls_tma_row_tones<NPS, T>(), static_cast<cuuint32_t>(NLTF)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(a.Y), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(e, MAMIMO_ERR_CUDA, "cuTensorMapEncodeTiled (LS) failed: " + std::to_string(r));
-  constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES, NPS>();
+  constexpr int smem = ls_tma_smem_bytes<NLTF, STAGES, NPS, T>();
   // per launch, not cached in a static: the attribute is per device and a process may hold engines on several
-  CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES, NPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int n_tiles = (a.n_sc + 63) / 64;
+  CK(e, cudaFuncSetAttribute(ls_tma_kernel<S, NLTF, STAGES, NPS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int n_tiles = (a.n_sc + T - 1) / T;
   const long long total = static_cast<long long>(a.n_pkt) * a.n_rx * n_tiles;
-  const int per_sm = std::max(1, std::min(e->ls_tma_ctas, (227 * 1024) / (smem + 1024)));
+  const int want_ctas = T == 32 ? std::max(e->ls_tma_ctas, 6) : e->ls_tma_ctas;
+  const int per_sm = std::max(1, std::min(want_ctas, (227 * 1024) / (smem + 1024)));
   const int sms = e->ls_sm_limit > 0 ? std::min(e->ls_sm_limit, e->num_sms) : e->num_sms;
   const int grid = static_cast<int>(std::min<long long>(total, static_cast<long long>(sms) * per_sm));
   {
     ProfScope ps(e, st, e->ls_prof_cls);
-    ls_tma_kernel<S, NLTF, STAGES, NPS><<<grid, 64 * (NLTF / 16), smem, st>>>(map, a);
+    ls_tma_kernel<S, NLTF, STAGES, NPS, T><<<grid, T * (NLTF / 16), smem, st>>>(map, a);
   }
   CK(e, cudaGetLastError());
   e->stats.kernel_launches++;
@@ -422,6 +426,7 @@ mamimo_status launch_ls(mamimo_engine* e, const LsArgs& a, cudaStream_t st) {
     const bool comb_ok = (a.n_sc % 64) == 0 && (a.kpad & 3) == 0 && a.n_pil >= 2;
 #define LS_TMA_CASE(NPS)                                                                        \
   return a.n_ltf == 32 ? launch_ls_tma<S, 32, 2, NPS>(e, a, st) : launch_ls_tma<S, 64, 2, NPS>(e, a, st);
+    if (a.n_ps == 1 && a.n_ltf == 64 && e->ls_tile64 == 32) return launch_ls_tma<S, 64, 2, 1, 32>(e, a, st);
     if (a.n_ps == 1) { LS_TMA_CASE(1) }
     if (comb_ok && a.n_ps == 2) { LS_TMA_CASE(2) }
     if (comb_ok && a.n_ps == 4) { LS_TMA_CASE(4) }
@@ -1059,6 +1064,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_SMALL_OVERLAP")) { e->small_batch_overlap = atoi(env) != 0; e->always_overlap = atoi(env) != 1; }
   if (const char* env = getenv("MAMIMO_LS_TMA")) e->ls_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_VERIFY")) e->ls_verify = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_LS_TILE64")) e->ls_tile64 = atoi(env) == 32 ? 32 : 64;
   if (const char* env = getenv("MAMIMO_OFDM_TMA")) e->ofdm_tma = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_LS_TMA_CTAS")) if (atoi(env) > 0) e->ls_tma_ctas = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_TILE")) e->ls_tile = atoi(env) == 128 ? 128 : 64;

@@ -393,14 +393,17 @@ __global__ void __launch_bounds__(T * (NLTF / 16)) ls_had_split_kernel(const LsA
 // NPS > 1 (comb pilots, the north_star's interpolation stage): the stage rows hold 72 tones, i.e. the tile plus the
 // halo pilot the last segment interpolates towards; only the pilot columns are despread (in place), and the emit
 // phase interpolates linearly between neighbouring pilots (same arithmetic as the generic kernel / oracle.interp).
-template <int NPS>
-__host__ __device__ constexpr int ls_tma_row_tones() { return NPS == 1 ? 64 : 72; }
-template <int NLTF, int STAGES, int NPS>
-constexpr int ls_tma_smem_bytes() { return STAGES * NLTF * ls_tma_row_tones<NPS>() * 8 + STAGES * 8 + 128; }
+// T = tones per tile: 64, or 32 for 64 antennas without comb pilots (16 KB stages instead of 32 KB: 6 resident CTAs per
+// SM instead of 3 -- the 64-antenna case was occupancy-limited at 73-78 % of the HBM peak)
+template <int NPS, int T = 64>
+__host__ __device__ constexpr int ls_tma_row_tones() { return NPS == 1 ? T : T + 8; }
+template <int NLTF, int STAGES, int NPS, int T = 64>
+constexpr int ls_tma_smem_bytes() { return STAGES * NLTF * ls_tma_row_tones<NPS, T>() * 8 + STAGES * 8 + 128; }
 
-template <int S, int NLTF, int STAGES, int NPS>
-__global__ void __launch_bounds__(64 * (NLTF / 16)) ls_tma_kernel(const __grid_constant__ CUtensorMap tmap_y, const LsArgs a) {
-  constexpr int BLK = 16, NB = NLTF / BLK, T = 64, TW = ls_tma_row_tones<NPS>(), PT = T / NPS;
+template <int S, int NLTF, int STAGES, int NPS, int T = 64>
+__global__ void __launch_bounds__(T * (NLTF / 16)) ls_tma_kernel(const __grid_constant__ CUtensorMap tmap_y, const LsArgs a) {
+  static_assert(T == 64 || (T == 32 && NPS == 1), "the comb-pilot emit path is written for 64-tone tiles");
+  constexpr int BLK = 16, NB = NLTF / BLK, TW = ls_tma_row_tones<NPS, T>(), PT = T / NPS;
   extern __shared__ uint8_t sm_ls_raw[];
   float2* in = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(sm_ls_raw) + 127) & ~static_cast<uintptr_t>(127));
   uint64_t* full = reinterpret_cast<uint64_t*>(in + STAGES * NLTF * TW);
