@@ -393,6 +393,35 @@ def test_ls_provisional_scale_is_verified_and_repaired(spike):
     assert rel_l2(ref_r, Hr2) <= TOL_DNN and rel_l2(ref_i, Hi2) <= TOL_DNN
 
 
+@pytest.mark.parametrize("kind", ["zeros", "one_tone", "denormal", "huge"])
+def test_fp16_automatic_scale_degenerate_inputs(kind):
+    """Corner cases of the device-side range bookkeeping: an all-zero batch (amax = 0), a batch with a single non-zero
+    sample, amplitudes near the bottom (1e-38) and near the top (1e30) of the float range -- finite planes equal to the
+    oracle's, no range error (fp32 has the range, so fp16x3 must not lose it)."""
+    nt, nr, nsc, npkt, hidden = 32, 2, 256, 2, (256, 192)
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    Y, _ = mm.synth.make_packets(46, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    if kind == "zeros":
+        Y = np.zeros_like(Y)
+    elif kind == "one_tone":
+        Y = np.zeros_like(Y)
+        Y[1, 0, 3, 17] = 0.25 - 2.0j
+    elif kind == "denormal":
+        Y = (Y * np.float32(1e-38)).astype(np.complex64)
+    else:
+        Y = (Y * np.float32(1e30)).astype(np.complex64)
+    with mm.Engine(nt, nr, nsc, hidden=hidden, precision="fp16x3") as eng:
+        eng.set_pilots(x, None)
+        eng.load_weights(nets)
+        Hr, Hi, Hls = eng.estimate(Y, want_ls=True)
+    assert np.isfinite(Hr).all() and np.isfinite(Hi).all()
+    ref_ls, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
+    if kind != "zeros":
+        assert rel_l2(ref_ls, Hls) <= (1e-5 if kind == "denormal" else TOL_LS)        # fp32 itself is subnormal at 1e-38/32
+    assert rel_l2(ref_r, Hr) <= TOL_DNN and rel_l2(ref_i, Hi) <= TOL_DNN, (kind, rel_l2(ref_r, Hr), rel_l2(ref_i, Hi))
+
+
 def test_mixed_amplitude_batch_per_packet_accuracy():
     """One batch holding packets 0, 40 and 60 dB apart (users at different path loss): every PACKET, not only the
     batch as a whole, stays within 1e-5 with the per-call automatic scale (no biases: the worst case)."""
