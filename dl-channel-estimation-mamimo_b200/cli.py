@@ -59,7 +59,7 @@ def build_parser():
     p.add_argument("--onlyReal", action="store_true")
     p.add_argument("--onlyImag", action="store_true")
     # engine knobs (not in the reference)
-    p.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp16x3", "fp32_simt"])
+    p.add_argument("--precision", default="fp16x3", choices=["tf32x3", "fp16x3", "fp32_simt"])
     p.add_argument("--chunk-pkts", default=64, type=int, help="packets per engine call")
     return p
 

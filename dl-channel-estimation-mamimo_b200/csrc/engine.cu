@@ -140,6 +140,8 @@ struct mamimo_engine {
   double gather_growth = 1.2;   // size ratio of consecutive sub-batches (see mamimo_estimate_stages)
   bool gather_ce = false;       // MAMIMO_GATHER_MODE=ce: the sub-batches' planes travel by copy engine (peer memcpy on per-peer
                                 // streams) instead of TMA stores from the final-layer kernels; SMs only compute
+  bool gather_push = false;     // MAMIMO_GATHER_MODE=push: like ce, but peer_push_kernel (push_ctas CTAs on the side stream)
+  int push_ctas = 24;           //   moves the rows with bulk copies instead of the copy engines
   cudaStream_t s_copy[kMaxGatherRanks] = {};
   cudaEvent_t ev_copy[kMaxGatherRanks] = {};
   int gather_sub = 1;           // > 1: pipelined step -- the batch is cut into this many sub-batches and the gathering
@@ -954,7 +956,7 @@ void mamimo_config_init(mamimo_config* c) {
   memset(c, 0, sizeof(*c));
   c->abi_version = MAMIMO_ABI_VERSION;
   c->n_ps = 1;
-  c->precision = MAMIMO_PREC_TF32X3;
+  c->precision = MAMIMO_PREC_FP16X3;   /* range-managed on the device (act_scale_log2 = 0): same 2e-6 as TF32X3 at twice the rate */
   c->input_mode = MAMIMO_INPUT_LS;
   c->act_scale_log2 = 0;   /* auto */
 }
@@ -1403,7 +1405,8 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
   // packets per 256-row pair tile: sub-batch boundaries must fall on whole tiles
   const int pkt_align = (2 * kFcBlockM) / std::gcd(2 * kFcBlockM, e->rows_per_pkt);
   const bool tc_pair = e->fc_pair && e->cfg.precision != MAMIMO_PREC_FP32_SIMT;
-  const bool ce_mode = gather && stages == all && e->gather_ce && tc_pair && e->n_layers >= 1;
+  const bool ce_mode = gather && stages == all && (e->gather_ce || e->gather_push) && tc_pair && e->n_layers >= 1;
+  const bool push_mode = ce_mode && e->gather_push;
   const bool pipelined = ce_mode || (gather && stages == all && e->gather_sub > 1 && e->gather_sms > 0 && e->n_layers >= 2 &&
                                      tc_pair && n_pkt >= 2LL * pkt_align);
   auto stage = [&](int64_t n, const void* in0, const void*, void* hls, float* hr, float* hi, cudaStream_t st) {
@@ -1453,6 +1456,10 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
           const size_t slot_off = (static_cast<size_t>(e->gather_rank) * e->gather_rows + e->cur_row_off) * e->cfg.d_out;
           float* own_r = e->gather_local[0] + slot_off;
           float* own_i = e->gather_local[1] + slot_off;
+          if (push_mode) {                                    // the push kernel of sub-batch i-1 holds push_ctas SMs
+            e->fc_sms = i == 0 ? full : std::max(2, (full - e->push_ctas) & ~1);
+            e->ls_sm_limit = i == 0 ? 0 : e->num_sms - e->push_ctas;
+          }
           s = dyn_begin(e, y_i, static_cast<size_t>(np_i) * e->cfg.n_rx * e->cfg.n_ltf * e->cfg.n_sc * 2, nullptr, 0,
                         y_type == MAMIMO_C128, st, true);
           if (s == MAMIMO_OK) s = DISPATCH_S(e, (run_ls<S>(e, y_i, y_type == MAMIMO_C128, static_cast<int>(np_i), hls_i, 0, true, st)));
@@ -1460,6 +1467,22 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
           if (s != MAMIMO_OK) break;
           CK(e, cudaEventRecord(e->ev_sub[i], st));
           const size_t bytes = static_cast<size_t>(rows_i) * e->cfg.d_out * sizeof(float);
+          if (push_mode) {
+            CK(e, cudaStreamWaitEvent(e->s_side, e->ev_sub[i], 0));
+            for (int d = 0; d < 2; ++d) {
+              PushArgs pa{};
+              pa.src = reinterpret_cast<const uint8_t*>(d ? own_i : own_r);
+              for (int p = 0; p < e->gather_world; ++p)
+                if (p != e->gather_rank) pa.dst[pa.n_dst++] = reinterpret_cast<uint8_t*>(e->gather_peer[d][p] + slot_off);
+              pa.bytes = bytes;
+              pa.flags = e->d_flags;
+              if (pa.n_dst) {
+                ProfScope ps(e, e->s_side, kClsStage);
+                peer_push_kernel<<<e->push_ctas, 32, kPushSmem, e->s_side>>>(pa);
+                CK(e, cudaGetLastError());
+              }
+            }
+          } else
           for (int p = 0; p < e->gather_world; ++p) {
             if (p == e->gather_rank) continue;
             CK(e, cudaStreamWaitEvent(e->s_copy[p], e->ev_sub[i], 0));
@@ -1486,6 +1509,11 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
       }
       e->fc_sms = full; e->ls_sm_limit = 0; e->dyn_slot = 0; e->cur_row_off = 0;
       if (s != MAMIMO_OK) return s;
+      if (push_mode) {
+        CK(e, cudaEventRecord(e->ev_side[1], e->s_side));
+        CK(e, cudaStreamWaitEvent(st, e->ev_side[1], 0));
+        return MAMIMO_OK;
+      }
       if (ce_mode) {
         for (int p = 0; p < e->gather_world; ++p) {
           if (p == e->gather_rank) continue;
@@ -1693,7 +1721,13 @@ mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, 
   if (const char* env = getenv("MAMIMO_GATHER_SMS")) e->gather_sms = atoi(env) & ~1;
   if (e->gather_sms >= e->fc_sms - 2) e->gather_sms = 0;
   // pipelined step (sub-batches): NVLink busy under the next sub-batch's LS + hidden layers
-  if (const char* env = getenv("MAMIMO_GATHER_MODE")) e->gather_ce = strcmp(env, "ce") == 0;
+  if (const char* env = getenv("MAMIMO_GATHER_MODE")) {
+    e->gather_ce = strcmp(env, "ce") == 0;
+    e->gather_push = strcmp(env, "push") == 0;
+  }
+  if (const char* env = getenv("MAMIMO_PUSH_CTAS")) e->push_ctas = std::max(1, std::min(atoi(env), e->num_sms - 4));
+  if (e->gather_push)
+    CK(e, cudaFuncSetAttribute(peer_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmem));
   if (e->gather_ce)
     for (int p = 0; p < world; ++p) {
       if (p == e->gather_rank || e->s_copy[p]) continue;

@@ -672,6 +672,60 @@ fc_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// Push variant of the all-gather (MAMIMO_GATHER_MODE=push): the final layers run the plain (3-stage) kernel into this
+// rank's own slot of its gathered planes, and this kernel -- a few CTAs on a side stream -- streams the finished rows
+// to the same slot of every peer's plane over NVLink with bulk copies (global -> shared -> peer global), while the
+// other SMs compute the next sub-batch.  One thread per CTA drives a ring of kPushBufs buffers: the load of chunk
+// i+1 is in flight while the stores of chunk i to all peers drain.
+constexpr int kPushChunk = 32 * 1024;
+constexpr int kPushBufs = 4;
+constexpr int kPushSmem = kPushBufs * kPushChunk + 128;
+struct PushArgs {
+  const uint8_t* src;                 // first byte of the rows to send (this rank's slot)
+  uint8_t* dst[kMaxGatherRanks];      // the same position in every peer's plane
+  int n_dst;
+  unsigned long long bytes;           // multiple of 16
+  uint32_t* flags;
+};
+
+__global__ void __launch_bounds__(32) peer_push_kernel(const PushArgs a) {
+  extern __shared__ uint8_t push_raw[];
+  uint8_t* buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(push_raw) + 127) & ~static_cast<uintptr_t>(127));
+  __shared__ uint64_t full[kPushBufs];
+  __shared__ uint32_t cta_abort;
+  if (threadIdx.x != 0) return;
+  cta_abort = 0;
+  for (int b = 0; b < kPushBufs; ++b) mbar_init(&full[b], 1);
+  fence_barrier_init();
+  const long long n_chunks = static_cast<long long>((a.bytes + kPushChunk - 1) / kPushChunk);
+  auto chunk_bytes = [&](long long c) {
+    const unsigned long long off = static_cast<unsigned long long>(c) * kPushChunk;
+    return static_cast<uint32_t>(a.bytes - off < static_cast<unsigned long long>(kPushChunk) ? a.bytes - off : kPushChunk);
+  };
+  long long it = 0, prev = -1;
+  for (long long c = blockIdx.x; ; c += gridDim.x, ++it) {
+    const bool have = c < n_chunks;
+    if (have) {
+      const int b = static_cast<int>(it % kPushBufs);
+      tma_store_wait_read<kPushBufs - 2>();          // the stores that last read buffer b (4 iterations ago) are done with it
+      mbar_arrive_expect_tx(&full[b], chunk_bytes(c));
+      bulk_load_1d(buf + b * kPushChunk, a.src + static_cast<unsigned long long>(c) * kPushChunk, chunk_bytes(c), &full[b]);
+    }
+    if (prev >= 0) {                                  // chunk of the previous iteration: landed -> send to every peer
+      const long long pit = it - 1;
+      const int b = static_cast<int>(pit % kPushBufs);
+      if (!mbar_wait(&full[b], static_cast<uint32_t>((pit / kPushBufs) & 1), &cta_abort, a.flags)) return;
+      const unsigned long long off = static_cast<unsigned long long>(prev) * kPushChunk;
+      for (int p = 0; p < a.n_dst; ++p) bulk_store_1d(a.dst[p] + off, buf + b * kPushChunk, chunk_bytes(prev));
+      tma_store_commit();
+    }
+    if (!have) break;
+    prev = c;
+  }
+  tma_store_wait_all<0>();
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact FP32 CUDA-core GEMM: 128x128 tile, 256 threads, 8x8 micro-tile, BK = 16.
 // A [rows_alloc][kpad] and W [Npad][kpad] are both K-major and zero padded, so no K masking.
 template <int S>

@@ -75,7 +75,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     g_cfg.n_sc = field_int(prhs[1], "n_sc", 0);
     g_cfg.n_ltf = field_int(prhs[1], "n_ltf", g_cfg.n_tx);
     g_cfg.n_ps = field_int(prhs[1], "n_ps", 1);
-    g_cfg.precision = field_int(prhs[1], "precision", MAMIMO_PREC_TF32X3);
+    g_cfg.precision = field_int(prhs[1], "precision", MAMIMO_PREC_FP16X3);
     g_cfg.d_out = field_int(prhs[1], "d_out", 0);
     g_cfg.d_in = g_cfg.d_out > 0 ? g_cfg.n_sc : 0;
     const mxArray* h = mxGetField(prhs[1], 0, "hidden");

@@ -116,6 +116,12 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 1-D bulk copy shared -> global (bulk async group; 16-byte aligned addresses and size)
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
 // 2-D tile -> L2 only (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),

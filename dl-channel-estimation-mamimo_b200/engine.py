@@ -58,7 +58,7 @@ class Engine:
     """One engine per device.  See include/mamimo.h for the contract of every call."""
 
     def __init__(self, n_tx, n_rx, n_sc, n_ltf=None, n_ps=1, hidden=(1024, 1024), d_in=None, d_out=None,
-                 input_mode="ls", precision="tf32x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=0,
+                 input_mode="ls", precision="fp16x3", max_pkts=0, device=0, len_ltf=0, act_scale_log2=0,
                  mlp=True, kb_per_chunk=0, host_chunk_pkts=0, fc_single_cta=False, fc_sm_reserve=0):
         cfg = _capi.Config()
         lib.mamimo_config_init(C.byref(cfg))
@@ -561,7 +561,7 @@ class CSIPredictor:
     or the nets are given directly as nets={'real': layers, 'imag': layers}.
     """
 
-    def __init__(self, model_path=None, experiment="RICE_RENEW", verbose=False, nets=None, precision="tf32x3",
+    def __init__(self, model_path=None, experiment="RICE_RENEW", verbose=False, nets=None, precision="fp16x3",
                  device=0):
         self.path = model_path
         self.experiment = experiment

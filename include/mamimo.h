@@ -61,8 +61,10 @@ typedef enum { MAMIMO_MEM_HOST = 0, MAMIMO_MEM_DEVICE = 1 } mamimo_mem;
 /* arithmetic of the FC layers (accumulation is always FP32) */
 typedef enum {
   MAMIMO_PREC_FP32_SIMT = 0,   /* CUDA-core FFMA, exact FP32: on-device accuracy anchor */
-  MAMIMO_PREC_TF32X3 = 1,      /* tcgen05 kind::tf32, error-compensated hi/lo split, 3 MMA passes */
-  MAMIMO_PREC_FP16X3 = 2,      /* tcgen05 kind::f16 (fp16), scaled hi/lo split, 3 MMA passes */
+  MAMIMO_PREC_TF32X3 = 1,      /* tcgen05 kind::tf32, error-compensated hi/lo split, 3 MMA passes; bitwise independent of how a
+                                  batch is chunked */
+  MAMIMO_PREC_FP16X3 = 2,      /* DEFAULT.  tcgen05 kind::f16 (fp16), hi/lo split scaled by device-chosen powers of two
+                                  (act_scale_log2), 3 MMA passes: same accuracy as TF32X3 at twice the MMA rate */
   MAMIMO_PREC_BF16X1 = 3       /* tcgen05 kind::f16 (bf16), single pass -- NOT within 1e-5; diagnostics only */
 } mamimo_precision;
 

@@ -793,7 +793,8 @@ def test_estimate_from_time_domain_reference_numerology():
 
 
 # ------------------------------------------------------------------------------ fused all-gather (final FC layer -> peers)
-@pytest.mark.parametrize("gather_sms,gather_sub", [(0, 1), (36, 1), (36, 3), (56, 8), ("ce", 1), ("ce", 3), ("ce", 8)])
+@pytest.mark.parametrize("gather_sms,gather_sub", [(0, 1), (36, 1), (36, 3), (56, 8), ("ce", 1), ("ce", 3), ("ce", 8),
+                                                   ("push", 1), ("push", 3), ("push", 8)])
 @pytest.mark.parametrize("nt,nr,nsc,hidden,pkts", [(8, 2, 128, (128, 64), (5, 3)), (32, 4, 1024, (1024, 1024), (3, 3)),
                                                    (32, 4, 256, (256, 128), (9, 7)), (8, 2, 128, (128, 64), (70, 33))])
 def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sms, gather_sub, monkeypatch):
@@ -803,8 +804,8 @@ def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sm
     import torch
     # gather_sms > 0 forces the NVLink-bound schedule (real net's gathering layer on a side stream with few SMs,
     # concurrent with the imaginary net's hidden layers) that the engine picks by itself for world >= 3
-    if gather_sms == "ce":       # copy-engine variant: the sub-batches' planes travel by peer memcpy on per-peer streams
-        monkeypatch.setenv("MAMIMO_GATHER_MODE", "ce")
+    if gather_sms in ("ce", "push"):   # the sub-batches' planes travel by peer memcpy on per-peer streams ("ce") or by
+        monkeypatch.setenv("MAMIMO_GATHER_MODE", gather_sms)   # peer_push_kernel's bulk copies on the side stream ("push")
         gather_sms = 0
     monkeypatch.setenv("MAMIMO_GATHER_SMS", str(gather_sms))
     # gather_sub > 1: pipelined step -- sub-batches side by side in the operand buffers, the gathering layers of

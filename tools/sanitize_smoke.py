@@ -89,7 +89,7 @@ Yb, _ = mm.synth.make_packets(4, 8, 32, 4, 1024, snr_db=10.0, x_tones=mm.synth.m
 Yb = Yb.copy()
 Yb[2, 1, :, 50] *= 3e4                                          # unsampled spike: forces the repair pass
 netsb = mm.synth.make_nets(1024, (128,), 1024)
-for mode in ("fused", "ce"):
+for mode in ("fused", "ce", "push"):
     os.environ["MAMIMO_GATHER_MODE"], os.environ["MAMIMO_GATHER_SUB"], os.environ["MAMIMO_GATHER_SMS"] = mode, "3", "36"
     with mm.Engine(32, 4, 1024, hidden=(128,), precision="fp16x3") as eng:
         eng.set_pilots(mm.synth.make_pilots(1024), None)

@@ -7,8 +7,10 @@ port=29540
 for c in $combos; do
   sub=${c%%:*}; sms=${c##*:}
   port=$((port+1))
-  mode=fused; if [ "$sms" = "ce" ]; then mode=ce; fi
-  MAMIMO_GATHER_MODE=$mode MAMIMO_GATHER_SUB=$sub MAMIMO_GATHER_SMS=${sms/ce/0} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+  mode=fused; ctas=24; gsms=$sms
+  if [ "$sms" = "ce" ]; then mode=ce; gsms=0; fi
+  case "$sms" in push*) mode=push; ctas=${sms#push}; gsms=0;; esac      # "push24" = push variant with 24 CTAs
+  MAMIMO_GATHER_MODE=$mode MAMIMO_PUSH_CTAS=${ctas:-24} MAMIMO_GATHER_SUB=$sub MAMIMO_GATHER_SMS=$gsms python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
       --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline --no-e2e "$@" \
       > gpurun_out/${tag}_n${N}_sub${sub}_sms${sms}.json 2> gpurun_out/${tag}_n${N}_sub${sub}_sms${sms}.err
   python - <<PY
