@@ -299,9 +299,23 @@ def run_ours(args):
     #      all-reduce per step is the cross-rank completion signal a consumer would need.
     #  --gather nccl: NCCL all-gather of each plane; the real plane's gather overlaps the imaginary net and the
     #      FC kernels leave --sm-reserve SMs free so the NCCL kernel never blocks a persistent CTA.
-    fused = world > 1 and args.gather == "fused"
+    #  --gather mc: the planes live in symmetric memory with an NVSwitch multicast binding; a multimem.st stream on a
+    #      side stream sends every finished sub-batch ONCE and the switch replicates it into every rank's plane.
+    fused = world > 1 and args.gather in ("fused", "mc")
     gather_note = args.gather
-    if fused:
+    if fused and args.gather == "mc":
+        try:
+            g_real, g_imag, _ = mm.sharding.connect_symmetric_gather(eng, npkt, require_multicast=True)
+            okf = torch.ones(1, device=dev)
+        except Exception as ex:
+            okf = torch.zeros(1, device=dev)
+            gather_note = "fused (multicast unavailable: %s)" % str(ex)[:80]
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if okf.item() == 0:
+            args.gather = "fused"
+            if gather_note == "mc":
+                gather_note = "fused (multicast unavailable on a peer)"
+    if fused and args.gather == "fused":
         try:
             g_real, g_imag = mm.sharding.connect_fused_gather(eng, npkt)
             okf = torch.ones(1, device=dev)
@@ -311,8 +325,9 @@ def run_ours(args):
         dist.all_reduce(okf, op=dist.ReduceOp.MIN)     # every rank must take the same path
         if okf.item() == 0:
             fused = False
-            if gather_note == "fused":
+            if not gather_note.startswith("nccl"):
                 gather_note = "nccl (fused unavailable on a peer)"
+    if fused:
         flag = torch.zeros(1, device=dev)
     ALL = eng.STAGE_LS | eng.STAGE_NET_REAL | eng.STAGE_NET_IMAG
 
@@ -586,7 +601,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=500, help="packets per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how H-hat is all-gathered")
+    ap.add_argument("--gather", default="fused", choices=["fused", "mc", "nccl"], help="N>1: how H-hat is all-gathered")
     ap.add_argument("--sm-reserve", type=int, default=16, help="N>1: SMs left free for the concurrent NCCL kernels")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
                     help="c2 = BASELINE configs[1] (the bench line); c3 = configs[2] (3000 packets, 8 SNR levels); c4 = configs[3] "

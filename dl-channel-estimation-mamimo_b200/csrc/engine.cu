@@ -121,7 +121,9 @@ struct mamimo_engine {
   // fused all-gather (optional): gathered planes [world * gather_rows][d_out] float32 per rank
   int gather_world = 0, gather_rank = 0;
   int64_t gather_rows = 0;                 // rows per rank slot
-  float* gather_local[2] = {nullptr, nullptr};                       // this rank's gathered planes (owned)
+  float* gather_local[2] = {nullptr, nullptr};                       // this rank's gathered planes
+  bool gather_owned = true;                                          // false: attached (caller's memory, never freed here)
+  float* gather_mc[2] = {nullptr, nullptr};                          // NVSwitch multicast addresses of the planes (or null)
   float* gather_peer[2][kMaxGatherRanks] = {};                       // every rank's planes as mapped here
   // OFDM front-end (optional)
   int fft_len = 0, cp_len = 0, sym_offset = 0, n_twiddle = 0;
@@ -1157,7 +1159,7 @@ void mamimo_destroy(mamimo_engine* e) {
     cudaFree(e->d_dbg);
   }
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(e->gather_local[0]); fr(e->gather_local[1]);
+  if (e->gather_owned) { fr(e->gather_local[0]); fr(e->gather_local[1]); }
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
   fr(e->dP); fr(e->d_inv_den); fr(e->dPd); fr(e->d_inv_den_d); fr(e->d_flags); fr(e->d_dyn); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
   if (e->h_flags) cudaFreeHost(e->h_flags);
@@ -1469,7 +1471,16 @@ mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y, mamimo_cty
           const size_t bytes = static_cast<size_t>(rows_i) * e->cfg.d_out * sizeof(float);
           if (push_mode) {
             CK(e, cudaStreamWaitEvent(e->s_side, e->ev_sub[i], 0));
-            for (int d = 0; d < 2; ++d) {
+            for (int d = 0; d < 2 && e->gather_mc[0]; ++d) {       // multicast: one store stream, the switch replicates
+              PushMcArgs ma{};
+              ma.src = reinterpret_cast<const float4*>(d ? own_i : own_r);
+              ma.mc = reinterpret_cast<float4*>(e->gather_mc[d] + slot_off);
+              ma.n_vec = bytes / 16;
+              ProfScope ps(e, e->s_side, kClsStage);
+              peer_push_mc_kernel<<<e->push_ctas, kPushMcThreads, 0, e->s_side>>>(ma);
+              CK(e, cudaGetLastError());
+            }
+            for (int d = 0; d < 2 && !e->gather_mc[0]; ++d) {
               PushArgs pa{};
               pa.src = reinterpret_cast<const uint8_t*>(d ? own_i : own_r);
               for (int p = 0; p < e->gather_world; ++p)
@@ -1689,7 +1700,11 @@ mamimo_status mamimo_gather_create(mamimo_engine* e, int32_t world, int32_t rank
     return fail(e, MAMIMO_ERR_INVALID, "need 1 <= world <= 8, 0 <= rank < world, 1 <= pkts_per_rank <= max_pkts");
   CK(e, cudaSetDevice(e->cfg.device));
   e->gather_world = 0;
-  for (int n = 0; n < 2; ++n) { if (e->gather_local[n]) { cudaFree(e->gather_local[n]); e->gather_local[n] = nullptr; } }
+  for (int n = 0; n < 2; ++n) {
+    if (e->gather_local[n] && e->gather_owned) cudaFree(e->gather_local[n]);
+    e->gather_local[n] = nullptr; e->gather_mc[n] = nullptr;
+  }
+  e->gather_owned = true;
   e->gather_rank = rank;
   e->gather_rows = pkts_per_rank * e->rows_per_pkt;
   const size_t bytes = static_cast<size_t>(world) * e->gather_rows * e->cfg.d_out * sizeof(float);
@@ -1701,6 +1716,38 @@ mamimo_status mamimo_gather_create(mamimo_engine* e, int32_t world, int32_t rank
   *real_plane = e->gather_local[0];
   *imag_plane = e->gather_local[1];
   return MAMIMO_OK;
+}
+
+mamimo_status mamimo_gather_attach(mamimo_engine* e, int32_t world, int32_t rank, int64_t pkts_per_rank,
+                                   void* const* real_planes, void* const* imag_planes, void* mc_real, void* mc_imag) {
+  if (!e || !real_planes || !imag_planes) return MAMIMO_ERR_INVALID;
+  if (e->n_layers == 0) return fail(e, MAMIMO_ERR_STATE, "no MLP configured");
+  if (world < 1 || world > kMaxGatherRanks || rank < 0 || rank >= world || pkts_per_rank < 1 || pkts_per_rank > e->max_pkts)
+    return fail(e, MAMIMO_ERR_INVALID, "need 1 <= world <= 8, 0 <= rank < world, 1 <= pkts_per_rank <= max_pkts");
+  if ((mc_real == nullptr) != (mc_imag == nullptr)) return fail(e, MAMIMO_ERR_INVALID, "give both multicast addresses or neither");
+  for (int p = 0; p < world; ++p)
+    if (!real_planes[p] || !imag_planes[p] || ((reinterpret_cast<uintptr_t>(real_planes[p]) | reinterpret_cast<uintptr_t>(imag_planes[p])) & 127))
+      return fail(e, MAMIMO_ERR_INVALID, "peer planes must be non-null and 128-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(mc_real) | reinterpret_cast<uintptr_t>(mc_imag)) & 127)
+    return fail(e, MAMIMO_ERR_INVALID, "multicast addresses must be 128-byte aligned");
+  CK(e, cudaSetDevice(e->cfg.device));
+  for (int n = 0; n < 2; ++n) { if (e->gather_local[n] && e->gather_owned) cudaFree(e->gather_local[n]); }
+  e->gather_owned = false;
+  e->gather_local[0] = static_cast<float*>(real_planes[rank]);
+  e->gather_local[1] = static_cast<float*>(imag_planes[rank]);
+  e->gather_mc[0] = static_cast<float*>(mc_real);
+  e->gather_mc[1] = static_cast<float*>(mc_imag);
+  e->gather_rank = rank;
+  e->gather_rows = pkts_per_rank * e->rows_per_pkt;
+  e->gather_world = -world;
+  invalidate_graphs(e);
+  mamimo_status s = mamimo_gather_connect(e, real_planes, imag_planes);
+  // with multicast addresses the push schedule is the default: the links carry every row once
+  if (s == MAMIMO_OK && mc_real && getenv("MAMIMO_GATHER_MODE") == nullptr) {
+    e->gather_push = true;
+    if (getenv("MAMIMO_GATHER_SUB") == nullptr) e->gather_sub = 6;
+  }
+  return s;
 }
 
 mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, void* const* imag_planes) {

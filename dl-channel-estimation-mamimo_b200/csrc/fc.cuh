@@ -725,6 +725,36 @@ __global__ void __launch_bounds__(32) peer_push_kernel(const PushArgs a) {
   tma_store_wait_all<0>();
 }
 
+// Multicast form of the same step (planes attached with NVSwitch multicast addresses, mamimo_gather_attach): every
+// 16-byte vector is read once from this rank's slot and stored ONCE to the multicast address with multimem.st -- the
+// switch replicates it into every rank's plane, so a rank's egress link carries its rows once instead of world-1
+// times.  Coalesced: a warp covers 512 contiguous bytes per store instruction; kPushMcUnroll vectors per thread in
+// flight.
+constexpr int kPushMcThreads = 512;
+constexpr int kPushMcUnroll = 8;
+struct PushMcArgs {
+  const float4* src;        // this rank's slot in its own plane
+  float4* mc;               // the same position behind the multicast address
+  unsigned long long n_vec; // 16-byte vectors
+};
+__device__ __forceinline__ void multimem_st_v4(float4* mc, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint64_t>(mc)), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__global__ void __launch_bounds__(kPushMcThreads) peer_push_mc_kernel(const PushMcArgs a) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kPushMcThreads;
+  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kPushMcThreads + threadIdx.x;
+  for (; i + (kPushMcUnroll - 1) * stride < a.n_vec; i += kPushMcUnroll * stride) {
+    float4 v[kPushMcUnroll];
+#pragma unroll
+    for (int u = 0; u < kPushMcUnroll; ++u) v[u] = __ldcg(a.src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kPushMcUnroll; ++u) multimem_st_v4(a.mc + i + u * stride, v[u]);
+  }
+  for (; i < a.n_vec; i += stride) multimem_st_v4(a.mc + i, __ldcg(a.src + i));
+}
+
 // ------------------------------------------------------------------------------------------
 // Exact FP32 CUDA-core GEMM: 128x128 tile, 256 threads, 8x8 micro-tile, BK = 16.
 // A [rows_alloc][kpad] and W [Npad][kpad] are both K-major and zero padded, so no K masking.

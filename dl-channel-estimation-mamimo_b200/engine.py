@@ -159,6 +159,15 @@ class Engine:
         ai = (C.c_void_p * n)(*imag_ptrs)
         check(lib.mamimo_gather_connect(self._h, ar, ai), self._h)
 
+    def gather_attach(self, world, rank, pkts_per_rank, real_ptrs, imag_ptrs, mc_real=0, mc_imag=0):
+        """Gather over planes the caller allocated and mapped (mamimo_gather_attach); mc_* = NVSwitch multicast
+        addresses of the two planes or 0."""
+        ar = (C.c_void_p * world)(*real_ptrs)
+        ai = (C.c_void_p * world)(*imag_ptrs)
+        check(lib.mamimo_gather_attach(self._h, world, rank, pkts_per_rank, ar, ai, C.c_void_p(mc_real or None),
+                                       C.c_void_p(mc_imag or None)), self._h)
+        self._gather = (world, rank, pkts_per_rank, int(real_ptrs[rank]), int(imag_ptrs[rank]))
+
     def gather_planes(self):
         """This rank's gathered planes as torch CUDA tensors [world * pkts_per_rank * n_rx*n_tx, d_out] (no copy)."""
         import torch

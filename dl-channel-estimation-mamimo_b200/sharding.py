@@ -110,3 +110,40 @@ def connect_fused_gather(engine, pkts_per_rank, group=None):
     engine.gather_connect(reals, imags)
     dist.barrier(group)
     return engine.gather_planes()
+
+
+def connect_symmetric_gather(engine, pkts_per_rank, group=None, require_multicast=False):
+    """Same contract as connect_fused_gather, but the planes come from torch's symmetric-memory allocator
+    (cuMemCreate + peer mappings + an NVSwitch multicast binding when the fabric has one) and are handed to the engine
+    with mamimo_gather_attach.  With a multicast address every row leaves this GPU once (multimem.st) and the switch
+    replicates it.  Returns (real, imag, has_multicast); the tensors stay alive with the returned objects."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", engine.cfg.device)
+    n = world * pkts_per_rank * engine.rows_per_pkt * engine.cfg.d_out
+    pg = group if group is not None else dist.group.WORLD
+    planes, handles = [], []
+    for _ in range(2):
+        t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        t.zero_()
+        h = symm_mem.rendezvous(t, pg.group_name)
+        planes.append(t)
+        handles.append(h)
+    ptrs = []
+    for t, h in zip(planes, handles):
+        off = t.data_ptr() - int(h.buffer_ptrs[rank])
+        if off < 0 or off % 128:
+            raise RuntimeError("symmetric-memory tensor is not at a 128-byte offset of its buffer")
+        ptrs.append(([int(p) + off for p in h.buffer_ptrs], (int(h.multicast_ptr) + off) if h.multicast_ptr else 0))
+    has_mc = bool(ptrs[0][1] and ptrs[1][1])
+    if require_multicast and not has_mc:
+        raise RuntimeError("no NVSwitch multicast address for the gathered planes")
+    engine.gather_attach(world, rank, pkts_per_rank, ptrs[0][0], ptrs[1][0], ptrs[0][1] if has_mc else 0,
+                         ptrs[1][1] if has_mc else 0)
+    engine._symm = (planes, handles)               # keep the allocation and its mappings alive with the engine
+    torch.cuda.synchronize()
+    dist.barrier(group)
+    shape = (world * pkts_per_rank * engine.rows_per_pkt, engine.cfg.d_out)
+    return planes[0].view(shape), planes[1].view(shape), has_mc

@@ -199,6 +199,15 @@ MAMIMO_API mamimo_status mamimo_estimate_stages(mamimo_engine* e, const void* Y,
 MAMIMO_API mamimo_status mamimo_gather_create(mamimo_engine* e, int32_t world, int32_t rank, int64_t pkts_per_rank,
                                               float** real_plane, float** imag_plane);
 MAMIMO_API mamimo_status mamimo_gather_connect(mamimo_engine* e, void* const* real_planes, void* const* imag_planes);
+/* Same, over planes the CALLER allocated and mapped (e.g. a symmetric-memory allocator: cuMemCreate + peer mappings):
+ * real_planes[r] / imag_planes[r] = rank r's plane as mapped in this process, entry [rank] this rank's own; the
+ * engine never frees them.  mc_real / mc_imag: NVSwitch multicast addresses bound to all `world` planes
+ * (cuMulticastCreate / cuMulticastBindMem), or NULL.  With multicast addresses the gather is a multimem.st stream on
+ * a side stream -- every row leaves this GPU once and the switch replicates it -- unless MAMIMO_GATHER_MODE says
+ * otherwise. */
+MAMIMO_API mamimo_status mamimo_gather_attach(mamimo_engine* e, int32_t world, int32_t rank, int64_t pkts_per_rank,
+                                              void* const* real_planes, void* const* imag_planes, void* mc_real,
+                                              void* mc_imag);
 MAMIMO_API mamimo_status mamimo_ipc_export(const void* dev_ptr, uint8_t handle[MAMIMO_IPC_HANDLE_BYTES]);
 MAMIMO_API mamimo_status mamimo_ipc_open(const uint8_t handle[MAMIMO_IPC_HANDLE_BYTES], void** dev_ptr);
 MAMIMO_API mamimo_status mamimo_ipc_close(void* dev_ptr);

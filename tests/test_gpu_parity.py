@@ -853,6 +853,56 @@ def test_fused_all_gather_two_virtual_ranks(nt, nr, nsc, hidden, pkts, gather_sm
             e.close()
 
 
+@pytest.mark.parametrize("mode", ["fused", "push"])
+def test_gather_attach_caller_planes(mode, monkeypatch):
+    """mamimo_gather_attach: the gathered planes are the CALLER's memory (here torch tensors; on a multi-GPU box a
+    symmetric-memory allocation, sharding.connect_symmetric_gather) -- same result as the engine-owned planes, and the
+    engine must not free them."""
+    import torch
+    monkeypatch.setenv("MAMIMO_GATHER_MODE", mode)
+    monkeypatch.setenv("MAMIMO_GATHER_SUB", "3")
+    monkeypatch.setenv("MAMIMO_GATHER_SMS", "36")
+    nt, nr, nsc, hidden, pkts = 32, 4, 256, (256, 128), (9, 7)
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    ppr, rows = max(pkts), nt * nr
+    Y, _ = mm.synth.make_packets(12, sum(pkts), nt, nr, nsc, snr_db=10.0, x_tones=x)
+    planes = [[torch.zeros((2 * ppr * rows, nsc), device="cuda") for _ in range(2)] for _ in range(2)]   # [rank][real/imag]
+    engs = []
+    try:
+        for r in range(2):
+            e = mm.Engine(nt, nr, nsc, hidden=hidden, precision="fp16x3", act_scale_log2=6)
+            e.set_pilots(x, None)
+            e.load_weights(nets)
+            engs.append(e)
+        ref_r, ref_i = engs[0].estimate(Y)
+        for r, e in enumerate(engs):
+            e.gather_attach(2, r, ppr, [planes[q][0].data_ptr() for q in range(2)], [planes[q][1].data_ptr() for q in range(2)])
+        with pytest.raises(mm.MamimoError):                       # one multicast address without the other
+            engs[0].gather_attach(2, 0, ppr, [planes[q][0].data_ptr() for q in range(2)],
+                                  [planes[q][1].data_ptr() for q in range(2)], mc_real=planes[0][0].data_ptr())
+        engs[0].gather_attach(2, 0, ppr, [planes[q][0].data_ptr() for q in range(2)], [planes[q][1].data_ptr() for q in range(2)])
+        st = torch.cuda.current_stream().cuda_stream
+        lo = 0
+        for r, e in enumerate(engs):
+            Yd = torch.from_numpy(Y[lo:lo + pkts[r]]).cuda()
+            e.estimate_stages_raw(15, Yd.data_ptr(), 0, pkts[r], 0, 0, 0, st)
+            lo += pkts[r]
+        torch.cuda.synchronize()
+        for q in range(2):
+            gr, gi = planes[q][0].cpu().numpy(), planes[q][1].cpu().numpy()
+            lo = 0
+            for r in range(2):
+                sl = slice(r * ppr * rows, (r * ppr + pkts[r]) * rows)
+                assert np.array_equal(gr[sl], ref_r[lo * rows:(lo + pkts[r]) * rows])
+                assert np.array_equal(gi[sl], ref_i[lo * rows:(lo + pkts[r]) * rows])
+                lo += pkts[r]
+    finally:
+        for e in engs:
+            e.close()
+    assert float(planes[0][0].abs().sum()) > 0                    # still the caller's, still readable after close
+
+
 @pytest.mark.parametrize("precision", ["fp16x3", "tf32x3"])
 def test_mode_a_reference_literal_shapes(precision):
     """The shipped pipeline's own network shape (full_pipeline_maMIMO_DNNEst.sh:40,47): input = time-domain LTF
