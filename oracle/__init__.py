@@ -26,8 +26,11 @@ Pinning status (see DESIGN.md "Oracle"):
   with a numpy Keras stand-in) is pinned, and the layer arithmetic is anchored on BN-fold == unfused identities.
 * ``oracle.svd`` (first lines of omphybweights.m's getWeightsForSubcarrier) is PINNED on those lines executed by
   ``mini_matlab`` (``tests/golden/ref_svd.npz``), through the basis-independent invariants only.
+* ``oracle.omp`` (ompdecomp.m's loop and the precoding lines of omphybweights.m's getWeightsForSubcarrier) is PINNED on
+  that text executed by ``mini_matlab`` (``tests/golden/ref_omp.npz``): atom indices exactly, coefficients to 1e-12,
+  the early stop on an exactly representable residual.
 * ``oracle.interp`` has no reference counterpart at all (the reference always
   uses Nps = 1): **parity unpinned**, defined here.
 """
 
-from . import tables, ls, mlp, postproc, interp, lmmse, svd  # noqa: F401
+from . import tables, ls, mlp, postproc, interp, lmmse, svd, omp  # noqa: F401

@@ -361,7 +361,64 @@ def run_omp_svd_lines():
     return out
 
 
+# ---------------------------------------------------------------- 8. ompdecomp.m loop + omphybweights.m weights lines
+def run_omp_lines():
+    """ompdecomp's loop (pg/ompdecomp.m:98-121, default identity weight) and getWeightsForSubcarrier's precoding lines
+    (pg/omphybweights.m:178-179,196-197), taken from the reference text and executed by mini_matlab.  The argument
+    parsing / validation around them (inputParser, validateattributes) is replaced by a plain signature."""
+    from mini_matlab import MatlabFile
+    base = os.path.join(REF, "packet_generation/phased_arr")
+    omp = open(os.path.join(base, "ompdecomp.m"), encoding="latin-1").read().splitlines()
+    i0 = next(i for i, l in enumerate(omp) if l.strip() == "Watom_temp = complex(zeros(Nelem,Nsparsity));")
+    i1 = next(i for i, l in enumerate(omp) if l.strip() == "WatomIdx = WatomIdx_temp(1:Ns);")
+    size_line = next(l for l in omp if l.strip() == "[Nelem,Nw] = size(Wopt);")
+    loop = omp[i0:i1 + 1]
+    assert any(l.strip() == "while m <= Nsparsity && Errnorm > eps" for l in loop)
+    hyb = open(os.path.join(base, "omphybweights.m"), encoding="latin-1").read().splitlines()
+    j0 = next(i for i, l in enumerate(hyb) if l.strip() == "[Fbb,Frf] = ompdecomp(Fopt,At,'MaxSparsity',NtRF);")
+    assert hyb[j0 + 1].strip() == "Fbb = sqrt(Ns)*Fbb/norm(Frf*Fbb,'fro');"
+    outs = [l for l in hyb if l.strip() in ("Fbb_out = Fbb.';", "Frf_out = Frf.';")][:2]
+    assert len(outs) == 2
+    wrap = ("function [Wcoeff,Watom,WatomIdx,Errnorm] = ompdecomp(Wopt,Adict,pname,Nsparsity)\n" + size_line + "\n"
+            "W = eye(Nelem);\n" + "\n".join(loop) + "\nend\n"
+            "function [Fbb_out,Frf_out] = weights(Fopt,Ns,NtRF,At)\n" + hyb[j0] + "\n" + hyb[j0 + 1] + "\n" +
+            "\n".join(outs) + "\nend\n")
+    m = MatlabFile(wrap)
+    rng = np.random.default_rng(6707)
+    out = {}
+
+    def steer(nt, nrays):                                   # unit-modulus columns, like steervec's output
+        return np.exp(2j * np.pi * rng.random((nt, nrays)))
+
+    def orthonormal(nt, ns):
+        q, _ = np.linalg.qr(rng.standard_normal((nt, ns)) + 1j * rng.standard_normal((nt, ns)))
+        return q
+
+    cases = {"a": (8, 2, 3, 40, 6), "b": (32, 1, 1, 500, 6), "c": (16, 4, 4, 64, 4), "d": (32, 2, 8, 120, 3)}
+    for tag, (nt, ns, nrf, nrays, n) in cases.items():
+        At = steer(nt, nrays)
+        F = np.stack([orthonormal(nt, ns) for _ in range(n)])
+        fbb, frf, idx, err = [], [], [], []
+        for k in range(n):
+            c, a, ix, e = m.call("ompdecomp", [F[k], At, "MaxSparsity", float(nrf)], 4)
+            fo, ro = m.call("weights", [F[k], float(ns), float(nrf), At], 2)
+            fbb.append(fo); frf.append(ro); idx.append(np.asarray(ix).ravel()); err.append(float(np.asarray(e).real.item()))
+        out["At_" + tag], out["Fopt_" + tag] = At, F
+        out["Fbb_" + tag], out["Frf_" + tag] = np.stack(fbb), np.stack(frf)
+        out["idx_" + tag], out["err_" + tag] = np.stack(idx).astype(np.int64), np.asarray(err)
+        out["cfg_" + tag] = np.asarray([nt, ns, nrf, nrays, n])
+    # early stop: Fopt is exactly one dictionary column (entries in {1, j, -1, -j}: every product is exact)
+    nt, nrays = 16, 24
+    At = (1j) ** rng.integers(0, 4, size=(nt, nrays))
+    Fe = (At[:, 7] / np.sqrt(nt)).reshape(nt, 1)
+    c, a, ix, e = m.call("ompdecomp", [Fe, At, "MaxSparsity", 3.0], 4)
+    out["At_e"], out["Fopt_e"], out["coef_e"] = At, Fe, np.asarray(c)
+    out["idx_e"], out["err_e"] = np.asarray(ix).ravel().astype(np.int64), np.asarray(float(np.asarray(e).real.item()))
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(HERE, "ref_omp.npz"), **run_omp_lines())
     np.savez_compressed(os.path.join(HERE, "ref_svd.npz"), **run_omp_svd_lines())
     np.savez_compressed(os.path.join(HERE, "ref_ber_test_reader.npz"), **run_ber_test_reader())
     np.savez_compressed(os.path.join(HERE, "ref_matlab_ls_lmmse.npz"), **run_matlab_hot_path())

@@ -65,7 +65,7 @@ def _trim(a):
 _TOKEN = re.compile(r"""
     (?P<num>(\d+(\.(?![*/^'])\d*)?|\.\d+)([eE][+-]?\d+)?([ij](?![A-Za-z0-9_]))?) |
     (?P<id>[A-Za-z_]\w*) |
-    (?P<op>\.\*|\./|\.\^|\.'|==|~=|<=|>=|&&|\|\||[-+*/^'<>=~:,;()\[\]{}.@&|]) |
+    (?P<op>\.\*|\./|\.\^|\.'|==|~=|<=|>=|&&|\|\||[-+*/\\^'<>=~:,;()\[\]{}.@&|]) |
     (?P<str>"[^"]*") |
     (?P<ws>[ \t]+) |
     (?P<nl>\n)
@@ -237,6 +237,12 @@ class Parser:
             body = self.parse_block(("end",))
             self.expect("end")
             return ("for", var, rng, body)
+        if tok.kind == "id" and tok.text == "while":
+            self.next()
+            cond = self.parse_expr()
+            body = self.parse_block(("end",))
+            self.expect("end")
+            return ("while", cond, body)
         if tok.kind == "id" and tok.text == "if":
             self.next()
             branches, other = [], None
@@ -342,7 +348,7 @@ class Parser:
 
     def parse_mul(self):
         a = self.parse_unary()
-        while self.peek().text in ("*", "/", ".*", "./") and self.peek().kind == "op":
+        while self.peek().text in ("*", "/", "\\", ".*", "./") and self.peek().kind == "op":
             op = self.next().text
             a = ("bin", op, a, self.parse_unary())
         return a
@@ -543,6 +549,23 @@ class MatlabFile:
             return [np.swapaxes(A[0], 0, 1)]
         if name == "ctranspose":
             return [np.conj(np.swapaxes(A[0], 0, 1))]
+        if name == "max" and len(A) == 1:
+            x = A[0]
+            v = x.ravel(order="F") if min(x.shape) == 1 else None
+            if v is None:
+                raise MatlabError("max: only vectors are supported")
+            key = np.abs(v) if np.iscomplexobj(v) else v            # MATLAB compares complex numbers by magnitude
+            k = int(np.argmax(key))                                 # first maximum
+            return [mat(v[k]), mat(float(k + 1))]
+        if name == "diag" and len(A) == 1:
+            x = A[0]
+            if min(x.shape) == 1:
+                return [np.diag(x.ravel(order="F"))]
+            return [np.diag(x).reshape(-1, 1)]
+        if name == "norm" and len(A) == 2 and isinstance(A[1], str):
+            if A[1] != "fro":
+                raise MatlabError("norm: unsupported option %r" % A[1])
+            return [mat(np.sqrt(np.sum(np.abs(A[0]) ** 2)))]
         if name == "norm":
             x = A[0]
             if min(x.shape) == 1 or x.ndim > 2:
@@ -625,6 +648,13 @@ class MatlabFile:
                 for c in range(cols.shape[1]):
                     env[s[1]] = mat(cols[:, c].reshape(-1, 1) if cols.shape[0] > 1 else cols[0, c])
                     self._exec_block(s[3], env)
+            elif kind == "while":
+                guard = 0
+                while self._truth(self._eval(s[1], env)):
+                    self._exec_block(s[2], env)
+                    guard += 1
+                    if guard > 100000:
+                        raise MatlabError("while loop does not terminate")
             elif kind == "if":
                 done = False
                 for cond, body in s[1]:
@@ -752,6 +782,12 @@ class MatlabFile:
                 if _is_scalar(b):
                     return a / b
                 return np.linalg.solve(b.T, a.T).T                # A / B = A * inv(B)
+            if op == "\\":                                      # A \ B: square A -> LU solve (MATLAB's mldivide)
+                if _is_scalar(a):
+                    return b / a
+                if a.shape[0] != a.shape[1]:
+                    raise MatlabError("mldivide: only square systems are supported")
+                return np.linalg.solve(a, b)
             if op == "^":
                 if _is_scalar(a) and _is_scalar(b):
                     return np.power(a.astype(np.complex128) if (a.real < 0).any() else a, b)
