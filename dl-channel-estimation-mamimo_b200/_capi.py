@@ -53,7 +53,7 @@ SYMBOLS = [
     "mamimo_synchronize", "mamimo_poll_flags", "mamimo_get_stats", "mamimo_host_alloc", "mamimo_host_free",
     "mamimo_profile_begin", "mamimo_profile_end", "mamimo_get_debug_counters",
     "mamimo_set_ofdm", "mamimo_ofdm_demod", "mamimo_estimate_time", "mamimo_lmmse", "mamimo_tau_rms", "mamimo_svd",
-    "mamimo_gather_create", "mamimo_gather_connect", "mamimo_gather_attach", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
+    "mamimo_gather_create", "mamimo_gather_connect", "mamimo_gather_attach", "mamimo_set_steering_dictionary", "mamimo_omp", "mamimo_ipc_export", "mamimo_ipc_open", "mamimo_ipc_close",
 ]
 
 
@@ -97,6 +97,8 @@ def _load():
         "mamimo_lmmse": (i32, [vp, vp, i32, i64, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, i32, i32, vp]),
         "mamimo_tau_rms": (C.c_double, [C.POINTER(C.c_double), i32, i32]),
         "mamimo_svd": (i32, [vp, vp, i32, i64, vp, vp, i32, i32, vp]),
+        "mamimo_set_steering_dictionary": (i32, [vp, C.POINTER(C.c_double), i32]),
+        "mamimo_omp": (i32, [vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, i32, i32, vp]),
         "mamimo_gather_create": (i32, [vp, i32, i32, i64, C.POINTER(vp), C.POINTER(vp)]),
         "mamimo_gather_connect": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "mamimo_gather_attach": (i32, [vp, i32, i32, i64, C.POINTER(vp), C.POINTER(vp), vp, vp]),

@@ -19,6 +19,7 @@
 #include "ls.cuh"
 #include "ofdm.cuh"
 #include "svd.cuh"
+#include "omp.cuh"
 #include "tables.h"
 
 using namespace mm;
@@ -108,6 +109,14 @@ struct mamimo_engine {
   std::vector<double> hPd;      // the same tables in double (mamimo_set_pilots_f64; FP64 LS of the MATLAB-facing surface)
   double2* dPd = nullptr;
   double2* d_inv_den_d = nullptr;
+  // OMP hybrid-precoder consumer (omp.cuh): steering dictionary and per-chunk workspace
+  double2* d_omp_At = nullptr;      // [n_rays][n_tx]
+  double2* d_omp_AtcT = nullptr;    // conj, transposed, zero padded: [n_tx][n_rays_pad]
+  int omp_rays = 0, omp_rays_pad = 0;
+  double2* d_omp_wres = nullptr;
+  uint8_t* d_omp_active = nullptr;
+  size_t omp_wres_bytes = 0, omp_active_bytes = 0;
+  bool omp_generic = false;
   HostLayer hl[2][MAMIMO_MAX_HIDDEN + 1];
   DevLayer dl[2][MAMIMO_MAX_HIDDEN + 1];
   Operand act_in[2];            // layer-0 A operand per net
@@ -1162,6 +1171,7 @@ void mamimo_destroy(mamimo_engine* e) {
   if (e->gather_owned) { fr(e->gather_local[0]); fr(e->gather_local[1]); }
   fr(e->d_z[0]); fr(e->d_z[1]); fr(e->d_T[0]); fr(e->d_T[1]); fr(e->d_zero_bias);
   fr(e->dP); fr(e->d_inv_den); fr(e->dPd); fr(e->d_inv_den_d); fr(e->d_flags); fr(e->d_dyn); fr(e->d_twiddle); fr(e->d_tw256); fr(e->d_tw3); fr(e->d_kmap); fr(e->lm_M); fr(e->lm_Dinv); fr(e->lm_par); fr(e->lm_in); fr(e->lm_out); fr(e->d_bins); fr(e->d_ydemod);
+  fr(e->d_omp_At); fr(e->d_omp_AtcT); fr(e->d_omp_wres); fr(e->d_omp_active);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   for (int net = 0; net < 2; ++net) {
     fr(e->act_in[net].ptr);
@@ -2138,6 +2148,108 @@ mamimo_status mamimo_svd(mamimo_engine* e, const void* H, mamimo_ctype h_type, i
   // chunks of at most 65535 packets (grid.y); the host path additionally streams in host_chunk units
   return run_chunked(e, n_pkt, std::min<int64_t>(e->max_pkts, 65535), H, hb, nullptr, 0, V1, vb, static_cast<float*>(sigma),
                      nullptr, sb, mem, static_cast<cudaStream_t>(stream), stage);
+}
+
+mamimo_status mamimo_set_steering_dictionary(mamimo_engine* e, const double* At, int32_t n_rays) {
+  if (!e || !At) return MAMIMO_ERR_INVALID;
+  if (n_rays < 1 || n_rays > (1 << 20)) return fail(e, MAMIMO_ERR_INVALID, "need 1 <= n_rays <= 2^20");
+  const int nt = e->cfg.n_tx;
+  for (size_t i = 0; i < static_cast<size_t>(2) * n_rays * nt; ++i)
+    if (!std::isfinite(At[i])) return fail(e, MAMIMO_ERR_INVALID, "dictionary holds a non-finite value");
+  CK(e, cudaSetDevice(e->cfg.device));
+  CK(e, cudaDeviceSynchronize());
+  const int pad = (n_rays + kOmpTile - 1) / kOmpTile * kOmpTile;
+  std::vector<double> t(static_cast<size_t>(2) * nt * pad, 0.0);
+  for (int r = 0; r < n_rays; ++r)
+    for (int j = 0; j < nt; ++j) {
+      t[2 * (static_cast<size_t>(j) * pad + r)] = At[2 * (static_cast<size_t>(r) * nt + j)];
+      t[2 * (static_cast<size_t>(j) * pad + r) + 1] = -At[2 * (static_cast<size_t>(r) * nt + j) + 1];
+    }
+  if (e->d_omp_At) { cudaFree(e->d_omp_At); e->d_omp_At = nullptr; }
+  if (e->d_omp_AtcT) { cudaFree(e->d_omp_AtcT); e->d_omp_AtcT = nullptr; }
+  e->omp_rays = 0;
+  CK(e, cudaMalloc(&e->d_omp_At, sizeof(double2) * n_rays * nt));
+  CK(e, cudaMalloc(&e->d_omp_AtcT, sizeof(double2) * nt * pad));
+  CK(e, cudaMemcpy(e->d_omp_At, At, sizeof(double2) * n_rays * nt, cudaMemcpyHostToDevice));
+  CK(e, cudaMemcpy(e->d_omp_AtcT, t.data(), sizeof(double2) * nt * pad, cudaMemcpyHostToDevice));
+  e->omp_rays = n_rays; e->omp_rays_pad = pad;
+  return MAMIMO_OK;
+}
+
+mamimo_status mamimo_omp(mamimo_engine* e, const void* F, mamimo_ctype f_type, int32_t f_rows, int64_t n_pkt, int32_t ns,
+                         int32_t n_rf, int32_t* idx, float* err, void* Fbb, mamimo_ctype fbb_type, mamimo_mem mem,
+                         void* stream) {
+  if (!e) return MAMIMO_ERR_INVALID;
+  if (n_pkt < 0 || (n_pkt > 0 && (!F || !idx || !err || !Fbb))) return fail(e, MAMIMO_ERR_INVALID, "null buffer");
+  if (e->omp_rays < 1) return fail(e, MAMIMO_ERR_STATE, "no steering dictionary (mamimo_set_steering_dictionary)");
+  const int nt = e->cfg.n_tx, nsc = e->cfg.n_sc;
+  if (ns < 1 || ns > kOmpMaxNs || ns > f_rows || ns > nt) return fail(e, MAMIMO_ERR_INVALID, "need 1 <= ns <= min(8, f_rows, n_tx)");
+  if (n_rf < 1 || n_rf > kOmpMaxRf || n_rf > e->omp_rays) return fail(e, MAMIMO_ERR_INVALID, "need 1 <= n_rf <= min(8, n_rays)");
+  if (nt > kOmpMaxTx) return fail(e, MAMIMO_ERR_UNSUPPORTED, "mamimo_omp supports n_tx <= 100");
+  if ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(err) | reinterpret_cast<uintptr_t>(Fbb)) & 15)
+    return fail(e, MAMIMO_ERR_INVALID, "F, idx, err and Fbb must be 16-byte aligned");
+  CK(e, cudaSetDevice(e->cfg.device));
+  const size_t fb = static_cast<size_t>(f_rows) * nt * nsc * (f_type == MAMIMO_C128 ? 16 : 8);
+  const size_t bb = static_cast<size_t>(ns) * n_rf * nsc * (fbb_type == MAMIMO_C128 ? 16 : 8);
+  const size_t ib = static_cast<size_t>(n_rf) * nsc * 4;
+  // workspace: the residual of a chunk of packets (256 MB at most) and its active flags
+  const size_t wres_pkt = static_cast<size_t>(ns) * nt * nsc * sizeof(double2);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(e->max_pkts, 65535), (256u << 20) / wres_pkt));
+  const int64_t cmax = std::min<int64_t>(chunk, std::max<int64_t>(n_pkt, 1));
+  if (n_rf > 1 && e->omp_wres_bytes < cmax * wres_pkt) {
+    CK(e, cudaDeviceSynchronize());
+    if (e->d_omp_wres) cudaFree(e->d_omp_wres);
+    e->d_omp_wres = nullptr; e->omp_wres_bytes = 0;
+    CK(e, cudaMalloc(&e->d_omp_wres, cmax * wres_pkt));
+    e->omp_wres_bytes = cmax * wres_pkt;
+  }
+  if (e->omp_active_bytes < static_cast<size_t>(cmax) * nsc) {
+    CK(e, cudaDeviceSynchronize());
+    if (e->d_omp_active) cudaFree(e->d_omp_active);
+    e->d_omp_active = nullptr; e->omp_active_bytes = 0;
+    CK(e, cudaMalloc(&e->d_omp_active, static_cast<size_t>(cmax) * nsc));
+    e->omp_active_bytes = static_cast<size_t>(cmax) * nsc;
+  }
+  const size_t corr_smem = omp_corr_smem(nt, ns);
+  const int w_res = omp_w_resident(nt, ns) ? 1 : 0;
+  const int pf = (nt * kOmpTile + kOmpThreads - 1) / kOmpThreads;          // = ceil(n_tx / 4)
+  auto corr = pf <= 8 ? omp_corr_kernel<8> : (pf <= 16 ? omp_corr_kernel<16> : omp_corr_kernel<25>);
+  CK(e, cudaFuncSetAttribute(corr, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(corr_smem)));
+  CK(e, cudaFuncSetAttribute(omp_corr1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(omp_corr1_smem(nt))));
+  e->omp_generic = getenv("MAMIMO_OMP_GENERIC") != nullptr;     // diagnostics: the 4x4 kernel for Ns = 1 too
+  auto stage = [&](int64_t n, const void* in0, const void*, void* fbb, float* ix, float* er, cudaStream_t st) {
+    OmpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.F = in0; a.f_double = f_type == MAMIMO_C128; a.f_rows = f_rows;
+    a.Wres = e->d_omp_wres; a.AtcT = e->d_omp_AtcT; a.At = e->d_omp_At;
+    a.idx = reinterpret_cast<int32_t*>(ix); a.err = er; a.Fbb = fbb; a.fbb_double = fbb_type == MAMIMO_C128;
+    a.active = e->d_omp_active;
+    a.n_tx = nt; a.n_sc = nsc; a.n_rays = e->omp_rays; a.n_rays_pad = e->omp_rays_pad; a.ns = ns; a.n_rf = n_rf;
+    CK(e, cudaMemsetAsync(e->d_omp_active, 1, static_cast<size_t>(n) * nsc, st));
+    const dim3 grid_c((nsc + kOmpTile - 1) / kOmpTile, static_cast<unsigned>(n));
+    const dim3 grid_r((nsc + 127) / 128, static_cast<unsigned>(n));
+    const int need = std::max(ns, n_rf);
+    for (int r = 0; r < n_rf; ++r) {
+      a.round = r;
+      {
+        ProfScope ps(e, st, kClsStage);
+        if (ns == 1 && !e->omp_generic) omp_corr1_kernel<<<grid_c, kOmp1Threads, omp_corr1_smem(nt), st>>>(a);
+        else corr<<<grid_c, kOmpThreads, corr_smem, st>>>(a, w_res);
+      }
+      {
+        ProfScope ps(e, st, kClsStage);
+        if (need <= 1) omp_refit_kernel<1, 1><<<grid_r, 128, 0, st>>>(a);
+        else if (need <= 2) omp_refit_kernel<2, 2><<<grid_r, 128, 0, st>>>(a);
+        else if (need <= 4) omp_refit_kernel<4, 4><<<grid_r, 128, 0, st>>>(a);
+        else omp_refit_kernel<8, 8><<<grid_r, 128, 0, st>>>(a);
+      }
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches += 2;
+    }
+    return MAMIMO_OK;
+  };
+  return run_chunked(e, n_pkt, chunk, F, fb, nullptr, 0, Fbb, bb, reinterpret_cast<float*>(idx), err, ib, mem,
+                     static_cast<cudaStream_t>(stream), stage);
 }
 
 mamimo_status mamimo_synchronize(mamimo_engine* e) {

@@ -6,8 +6,8 @@
 //     H = Hin.';  [~,~,v] = svd(H);  Fopt = v(:,1:Ns);
 // Hin = squeeze(hDp(k,:,:)) is [Nt x Nr], so H is [Nr x Nt] with H(i,j) = hD(k,j,i) = H-hat[pkt][i_rx][j_tx][k].
 //
-// What is computed are the quantities that do NOT depend on LAPACK's choice of basis (the reference call site asks for
-// Ns = Nt columns of v, of which Nt - Nr span the null space in an arbitrary basis):
+// What is computed are the quantities that do NOT depend on LAPACK's choice of basis (v is Nt x Nt, of which Nt - Nr
+// columns span the null space in an arbitrary basis; the call site keeps Ns = numSTS of them, 1 as shipped):
 //   sigma[r]        the Nr singular values, descending
 //   V1[:, r]        the Nr dominant right singular vectors v_r = H^H u_r / sigma_r; each is unique up to a phase, the
 //                   projector V1 V1^H onto the row space of H and Fopt Fopt^H restricted to it are unique.

@@ -416,6 +416,63 @@ class Engine:
                              _capi.MEM_HOST, None), self._h)
         return (sig, V) if want_vectors else sig
 
+    # ------------------------------------------------------------------ OMP hybrid precoder (next row f-4, after svd)
+    def set_steering_dictionary(self, At):
+        """At [n_tx, n_rays] complex: the collection of candidate analog weights, column per ray, as MATLAB holds it
+        (pg/BER_test_maMIMO_LTF.m:365 `At = steervec(prm.posTxElem,txang)`)."""
+        At = np.asarray(At)
+        if At.ndim != 2 or At.shape[0] != self.cfg.n_tx:
+            raise ValueError("At must be [n_tx=%d, n_rays]" % self.cfg.n_tx)
+        rows = np.ascontiguousarray(At.T.astype(np.complex128))            # [n_rays][n_tx]
+        check(lib.mamimo_set_steering_dictionary(self._h, rows.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)),
+                                                 int(rows.shape[0])), self._h)
+        self._n_rays = int(rows.shape[0])
+
+    def omp(self, F, ns, n_rf, check_flags=True):
+        """Orthogonal matching pursuit of every tone's Fopt over the steering dictionary (pg/omphybweights.m:178-179 +
+        pg/ompdecomp.m:101-121).  F [n_pkt, f_rows >= ns, n_tx, n_sc] complex64/128 (rows 0..ns-1 = Fopt's columns; the V1
+        of svd() as it stands), numpy = host / torch CUDA = device ->
+        idx int32 [n_pkt, n_rf, n_sc] (0-based dictionary column, -1 after an early stop), err float32 [n_pkt, n_rf, n_sc]
+        (residual norm after each round), Fbb complex [n_pkt, ns, n_rf, n_sc] (= the reference's Fbb(k, s, j))."""
+        c = self.cfg
+        if F.ndim != 4 or tuple(F.shape[2:]) != (c.n_tx, c.n_sc) or F.shape[1] < ns:
+            raise ValueError("F must be [n_pkt, f_rows >= ns, n_tx=%d, n_sc=%d]" % (c.n_tx, c.n_sc))
+        n_pkt, f_rows = int(F.shape[0]), int(F.shape[1])
+        if _is_torch_cuda(F):
+            import torch
+            if F.dtype not in (torch.complex64, torch.complex128):
+                raise TypeError("F must be complex64 or complex128")
+            F = F.contiguous()
+            t = _capi.C128 if F.dtype == torch.complex128 else _capi.C64
+            idx = torch.empty((n_pkt, n_rf, c.n_sc), dtype=torch.int32, device=F.device)
+            err = torch.empty((n_pkt, n_rf, c.n_sc), dtype=torch.float32, device=F.device)
+            Fbb = torch.empty((n_pkt, ns, n_rf, c.n_sc), dtype=F.dtype, device=F.device)
+            st = torch.cuda.current_stream(F.device).cuda_stream
+            check(lib.mamimo_omp(self._h, C.c_void_p(F.data_ptr()), t, f_rows, n_pkt, ns, n_rf, C.c_void_p(idx.data_ptr()),
+                                 C.c_void_p(err.data_ptr()), C.c_void_p(Fbb.data_ptr()), t, _capi.MEM_DEVICE, C.c_void_p(st)),
+                  self._h)
+            if check_flags:
+                self.poll_flags(st)
+            return idx, err, Fbb
+        F = np.ascontiguousarray(F)
+        if F.dtype not in (np.complex64, np.complex128):
+            raise TypeError("F must be complex64 or complex128")
+        t = _capi.C128 if F.dtype == np.complex128 else _capi.C64
+        idx = np.empty((n_pkt, n_rf, c.n_sc), dtype=np.int32)
+        err = np.empty((n_pkt, n_rf, c.n_sc), dtype=np.float32)
+        Fbb = np.empty((n_pkt, ns, n_rf, c.n_sc), dtype=F.dtype)
+        check(lib.mamimo_omp(self._h, _np_ptr(F), t, f_rows, n_pkt, ns, n_rf, _np_ptr(idx), _np_ptr(err), _np_ptr(Fbb), t,
+                             _capi.MEM_HOST, None), self._h)
+        return idx, err, Fbb
+
+    def omp_precoder(self, H, ns, n_rf):
+        """[Fbb, Frf] = omphybweights(hD, Ns, NtRF, AtExp) for a batch (pg/BER_test_maMIMO_LTF.m:372): svd() then omp().
+        H [n_pkt, n_rx, n_tx, n_sc] -> (idx, err, Fbb) as omp(); the reference's Frf(k, j, :) is dictionary column
+        idx[p, j, k]."""
+        _, V = self.svd(H)
+        idx, err, Fbb = self.omp(V, ns, n_rf)
+        return idx, err, Fbb
+
     def debug_counters(self, reset=True):
         """role counters of the CTA-pair FC kernel (mamimo_get_debug_counters; debug build + MAMIMO_FC_DEBUG=1)"""
         out = (C.c_uint64 * 8)()

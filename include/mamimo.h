@@ -264,6 +264,25 @@ MAMIMO_API double mamimo_tau_rms(const double* h, int32_t n, int32_t is_complex)
 MAMIMO_API mamimo_status mamimo_svd(mamimo_engine* e, const void* H, mamimo_ctype h_type, int64_t n_pkt, void* sigma,
                                     void* V1, mamimo_ctype out_type, mamimo_mem mem, void* stream);
 
+/* ---- next row (continued): orthogonal matching pursuit over a steering dictionary -----------------
+ * Replaces, for every (packet, tone) at once, the transmit side of getWeightsForSubcarrier after its SVD
+ * (pg/omphybweights.m:178-179: `[Fbb,Frf] = ompdecomp(Fopt,At,'MaxSparsity',NtRF); Fbb = sqrt(Ns)*Fbb/norm(Frf*Fbb,'fro')`)
+ * with ompdecomp.m:101-121's greedy loop (identity weight), as pg/BER_test_maMIMO_LTF.m:364-372 calls it: one
+ * dictionary At for all subcarriers of the batch.  FP64 arithmetic throughout.
+ *   set_steering_dictionary: At complex128 interleaved, HOST memory, [n_rays][n_tx] (row r = MATLAB's At(:, r+1)).
+ *   omp: F = Fopt, complex [n_pkt][f_rows][n_tx][n_sc] with rows 0..ns-1 used -- mamimo_svd's V1 as it stands
+ *        (f_rows = n_rx) or a tight tensor (f_rows = ns).  Outputs, tone index fastest like every tensor here:
+ *        idx  int32 [n_pkt][n_rf][n_sc]   0-based dictionary row chosen in round j; -1 after an early stop
+ *                                         (residual norm <= eps, ompdecomp.m:105).  Frf(k, j, :) = At row idx[j].
+ *        err  float [n_pkt][n_rf][n_sc]   Frobenius norm of Fopt - atoms*coeff after round j (the last = Errnorm)
+ *        Fbb  complex [n_pkt][ns][n_rf][n_sc] = the returned Fbb(k, s, j) (:196, scaled as :179); columns of rounds
+ *                                         not run are zero.  Defined up to Fopt's own phase / unitary freedom.
+ *   ns <= 8, n_rf <= 8, n_tx <= 100. */
+MAMIMO_API mamimo_status mamimo_set_steering_dictionary(mamimo_engine* e, const double* At, int32_t n_rays);
+MAMIMO_API mamimo_status mamimo_omp(mamimo_engine* e, const void* F, mamimo_ctype f_type, int32_t f_rows, int64_t n_pkt,
+                                    int32_t ns, int32_t n_rf, int32_t* idx, float* err, void* Fbb,
+                                    mamimo_ctype fbb_type, mamimo_mem mem, void* stream);
+
 /* Error reporting of DEVICE-buffer calls.  Every entry point taking mem == MAMIMO_MEM_DEVICE only enqueues work on
  * `stream` and returns; conditions its kernels detect (MAMIMO_ERR_RANGE, MAMIMO_ERR_TIMEOUT, LMMSE not-PD) are
  * latched in a device flag word and reported -- and cleared -- by the next mamimo_synchronize (waits for the whole

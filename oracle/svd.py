@@ -7,10 +7,10 @@ Hin = squeeze(Hchann_in(m,:,:)) = [Nt x Nr] from packet_generation/phased_arr/BE
 
     H = Hin.';                 % [Nr x Nt], plain transpose: H(i,j) = hD(k,j,i)           (:174)
     [~,~,v] = svd(H);          % v [Nt x Nt]                                               (:175)
-    Fopt = v(:,1:Ns);          % call site passes Ns = NtRF = numSTS = Nt                  (:176)
+    Fopt = v(:,1:Ns);          % call site passes Ns = NtRF = numSTS (BER_test :71 = sum(numSTSVec): 1 as shipped)  (:176)
 
-H has rank <= Nr < Nt, so columns Nr+1..Nt of v are an arbitrary (LAPACK-build-defined) basis of the null space and
-every column is only defined up to a phase.  The engine (mamimo_svd) therefore returns, and this oracle defines, the
+H has rank <= Nr < Nt, so columns Nr+1..Nt of v are an arbitrary (LAPACK-build-defined) basis of the null space (only
+Ns <= Nr is meaningful) and every column is only defined up to a phase.  The engine (mamimo_svd) therefore returns, and this oracle defines, the
 basis-independent content: the Nr singular values and the Nr dominant right singular vectors, compared through the
 projector V1 V1^H (and through sigma_r = ||H v_r||).
 

@@ -128,4 +128,13 @@ with mm.Engine(8, 2, 8, hidden=(64, 32), d_in=160 + 8, d_out=40, input_mode="tim
     a, b = eng.predict_time(rng.standard_normal((3, 2, 160)), rng.standard_normal((3, 2, 160)))
     assert np.isfinite(a).all()
 print("ok modes A/B auto scale")
+# OMP hybrid precoder: both correlation kernels (Ns = 1 tall block, general), resident and reloaded residual tiles,
+# every refit instantiation, ragged tone count
+for nt4, ns4, nrf4, nsc4 in ((32, 1, 3, 70), (8, 2, 2, 100), (64, 4, 4, 65), (64, 6, 8, 33)):
+    with mm.Engine(nt4, 8, nsc4, mlp=False) as eng:
+        eng.set_steering_dictionary(np.exp(2j * np.pi * rng.random((nt4, 150))))
+        Hq = (rng.standard_normal((2, 8, nt4, nsc4)) + 1j * rng.standard_normal((2, 8, nt4, nsc4))).astype(np.complex64)
+        ix, er, fb = eng.omp_precoder(Hq, ns4, nrf4)
+        assert (ix >= 0).all() and np.isfinite(fb).all() and np.isfinite(er).all()
+    print("ok omp", nt4, ns4, nrf4)
 print("sanitize smoke done")
