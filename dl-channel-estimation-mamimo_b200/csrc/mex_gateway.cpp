@@ -11,6 +11,11 @@
 //   mamimo_mex('ofdm', fftLen, cpLen, symOffset, carriers)   ofdmdemod parameters; carriers = prm.CarriersLocations
 //   Y = mamimo_mex('demod', x)                     x complex double [nltf*(fftLen+cpLen) x Nr (x Npkt)] (inputRXSig) ->
 //                                                  Y complex single [Nsc x nltf x Nr (x Npkt)] (= rxOFDM(:,1:nltf,:))
+//   [Fbb, Frf, idx] = mamimo_mex('omphyb', hD, Ns, NtRF, At)   precoding-only omphybweights (pg/omphybweights.m:1,150-163) for
+//                                                  all subcarriers: hD complex double [Nsc x Nt x Nr (x Npkt)], At [Nt x nRays] or
+//                                                  the reference's AtExp [Nsc x Nt x nRays] (page 1 is used: the call site repeats
+//                                                  one At, BER_test :366-369) -> Fbb [Nsc x Ns x NtRF], Frf [Nsc x NtRF x Nt],
+//                                                  idx [Nsc x NtRF] 1-based dictionary columns (0 = loop stopped before)
 //   ltf = mamimo_mex('ltf')                        256 x 1 tone table (no engine needed)
 //   mamimo_mex('destroy')
 //
@@ -184,6 +189,83 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     plhs[0] = mxCreateNumericArray(nd, d, mxDOUBLE_CLASS, mxCOMPLEX);
     fail(mamimo_lmmse(g_engine, mxGetComplexDoubles(hd), MAMIMO_C128, (int64_t)np, t_rms, snr,
                       mxGetComplexDoubles(plhs[0]), MAMIMO_C128, MAMIMO_MEM_HOST, NULL));
+  } else if (!strcmp(cmd, "omphyb")) {           // [Fbb,Frf] = omphybweights(Hchann_in,Ns,NtRF,At), pg/BER_test_maMIMO_LTF.m:372
+    need_engine();
+    if (nrhs < 5) mexErrMsgIdAndTxt("mamimo:usage", "[Fbb, Frf, idx] = mamimo_mex('omphyb', hD, Ns, NtRF, At)");
+    const mxArray* hd = prhs[1];
+    if (!mxIsComplex(hd) || !mxIsDouble(hd)) mexErrMsgIdAndTxt("mamimo:type", "hD must be complex double");
+    const mwSize nd = mxGetNumberOfDimensions(hd);
+    const mwSize* d = mxGetDimensions(hd);
+    const mwSize nsc = (mwSize)g_cfg.n_sc, nt = (mwSize)g_cfg.n_tx;
+    const mwSize nr = nd >= 3 ? d[2] : 1, np = nd >= 4 ? d[3] : 1;
+    if (nd > 4 || d[0] != nsc || d[1] != nt || nr != (mwSize)g_cfg.n_rx)
+      mexErrMsgIdAndTxt("mamimo:size", "hD must be [Nsc x Nt x Nr (x Npkt)] = [%d x %d x %d]", g_cfg.n_sc, g_cfg.n_tx, g_cfg.n_rx);
+    const int ns = (int)mxGetScalar(prhs[2]), nrf = (int)mxGetScalar(prhs[3]);
+    if (ns < 1 || ns > (int)nr || ns > nrf)      // omphybweights.m:116-117 (NS <= NTRF); rank(H) <= Nr
+      mexErrMsgIdAndTxt("mamimo:size", "need 1 <= NS <= min(NTRF, Nr)");
+    const mxArray* at = prhs[4];
+    if (!mxIsComplex(at) || !mxIsDouble(at)) mexErrMsgIdAndTxt("mamimo:type", "At must be complex double");
+    const mwSize and_ = mxGetNumberOfDimensions(at);
+    const mwSize* ad = mxGetDimensions(at);
+    mwSize n_rays = 0;
+    mxArray* at2 = NULL;                          // [Nt x nRays]: column-major == the engine's [ray][tx] rows
+    const mxComplexDouble* rows = NULL;
+    if (and_ == 2 && ad[0] == nt) {
+      n_rays = ad[1];
+      rows = mxGetComplexDoubles(at);
+    } else if (and_ == 3 && ad[0] == nsc && ad[1] == nt) {
+      n_rays = ad[2];
+      const mwSize dd[2] = {nt, n_rays};
+      at2 = mxCreateNumericArray(2, dd, mxDOUBLE_CLASS, mxCOMPLEX);
+      mxComplexDouble* w = mxGetComplexDoubles(at2);
+      const mxComplexDouble* src = mxGetComplexDoubles(at);
+      for (mwSize i = 0; i < nt * n_rays; ++i) w[i] = src[i * nsc];       // At(1, t, ray)
+      rows = w;
+    } else {
+      mexErrMsgIdAndTxt("mamimo:size", "At must be [Nt x nRays] or [Nsc x Nt x nRays]");
+    }
+    if (nrf > (int)n_rays) mexErrMsgIdAndTxt("mamimo:size", "NTRF exceeds the number of dictionary columns");
+    fail(mamimo_set_steering_dictionary(g_engine, (const double*)rows, (int32_t)n_rays));
+    const mwSize sd[3] = {nsc, nr, np};
+    mxArray* sig = mxCreateNumericArray(3, sd, mxDOUBLE_CLASS, mxREAL);
+    mxArray* v1 = mxCreateNumericArray(nd, d, mxDOUBLE_CLASS, mxCOMPLEX);
+    fail(mamimo_svd(g_engine, mxGetComplexDoubles(hd), MAMIMO_C128, (int64_t)np, mxGetDoubles(sig), mxGetComplexDoubles(v1),
+                    MAMIMO_C128, MAMIMO_MEM_HOST, NULL));
+    const mwSize id[3] = {nsc, (mwSize)nrf, np};
+    mxArray* ix = mxCreateNumericArray(3, id, mxSINGLE_CLASS, mxREAL);    // 4-byte cells: int32 indices
+    mxArray* er = mxCreateNumericArray(3, id, mxSINGLE_CLASS, mxREAL);
+    const mwSize fd[4] = {nsc, (mwSize)nrf, (mwSize)ns, np};
+    mxArray* fb = mxCreateNumericArray(4, fd, mxDOUBLE_CLASS, mxCOMPLEX);  // engine order [pkt][s][j][k]
+    fail(mamimo_omp(g_engine, mxGetComplexDoubles(v1), MAMIMO_C128, (int32_t)nr, (int64_t)np, ns, nrf,
+                    (int32_t*)mxGetSingles(ix), mxGetSingles(er), mxGetComplexDoubles(fb), MAMIMO_C128, MAMIMO_MEM_HOST, NULL));
+    const int32_t* sel = (const int32_t*)mxGetSingles(ix);
+    const mxComplexDouble* f = mxGetComplexDoubles(fb);
+    const mwSize od0[4] = {nsc, (mwSize)ns, (mwSize)nrf, np};             // Fbb(k, s, j): omphybweights.m:154,196
+    plhs[0] = mxCreateNumericArray(np > 1 ? 4 : 3, od0, mxDOUBLE_CLASS, mxCOMPLEX);
+    mxComplexDouble* o0 = mxGetComplexDoubles(plhs[0]);
+    for (mwSize p = 0; p < np; ++p)
+      for (mwSize j = 0; j < (mwSize)nrf; ++j)
+        for (mwSize q = 0; q < (mwSize)ns; ++q)
+          memcpy(o0 + ((p * nrf + j) * ns + q) * nsc, f + ((p * ns + q) * nrf + j) * nsc, nsc * sizeof(mxComplexDouble));
+    if (nlhs >= 2) {                                                       // Frf(k, j, t) = At(t, idx(k, j)): :155,197
+      const mwSize od1[4] = {nsc, (mwSize)nrf, nt, np};
+      plhs[1] = mxCreateNumericArray(np > 1 ? 4 : 3, od1, mxDOUBLE_CLASS, mxCOMPLEX);
+      mxComplexDouble* o1 = mxGetComplexDoubles(plhs[1]);
+      for (mwSize p = 0; p < np; ++p)
+        for (mwSize t = 0; t < nt; ++t)
+          for (mwSize j = 0; j < (mwSize)nrf; ++j)
+            for (mwSize k = 0; k < nsc; ++k) {
+              const int32_t c = sel[(p * nrf + j) * nsc + k];
+              if (c >= 0) o1[((p * nt + t) * nrf + j) * nsc + k] = rows[(mwSize)c * nt + t];
+            }
+    }
+    if (nlhs >= 3) {
+      plhs[2] = mxCreateNumericArray(np > 1 ? 3 : 2, id, mxDOUBLE_CLASS, mxREAL);
+      double* o2 = mxGetDoubles(plhs[2]);
+      for (mwSize i = 0; i < nsc * nrf * np; ++i) o2[i] = (double)(sel[i] + 1);
+    }
+    mxDestroyArray(sig); mxDestroyArray(v1); mxDestroyArray(ix); mxDestroyArray(er); mxDestroyArray(fb);
+    if (at2) mxDestroyArray(at2);
   } else {
     mexErrMsgIdAndTxt("mamimo:usage", "unknown command '%s'", cmd);
   }

@@ -140,3 +140,43 @@ def test_gateway_full_path_estimate_and_ofdm(mex):
     assert Yd.shape == (nsc, nt, nr, npkt) and Yd.dtype == np.complex64
     assert rel_l2(np.transpose(ofdm.ofdm_demod(x, 256, 64, 64, car), (3, 2, 1, 0)), Yd) <= 2e-6
     mex.call("destroy")
+
+
+@pytest.mark.gpu
+def test_gateway_omphybweights_precoding(mex):
+    """[Fbb, Frf, idx] = mamimo_mex('omphyb', hD, Ns, NtRF, AtExp): the call of pg/BER_test_maMIMO_LTF.m:372 with its own
+    argument shapes (hD [L x Nt x Nr], AtExp [L x Nt x nRays] = one dictionary repeated per subcarrier) against the oracle
+    of the reference's per-subcarrier loop: same columns, Frf = those dictionary columns, Frf.'*Fbb.' up to Fopt's phase."""
+    from oracle import omp as oomp
+    rng = np.random.default_rng(77)
+    L, nt, nr, nrays = 52, 16, 2, 90
+    hD = rng.standard_normal((L, nt, nr)) + 1j * rng.standard_normal((L, nt, nr))          # MATLAB [L x Nt x Nr]
+    At = np.exp(2j * np.pi * rng.random((nt, nrays)))
+    AtExp = np.broadcast_to(At[None], (L, nt, nrays)).copy()
+    with pytest.raises(MexError) as ei:
+        mex.call("omphyb", hD, 1.0, 1.0, AtExp, nlhs=2)                                    # no engine yet
+    assert ei.value.identifier == "mamimo:state"
+    mex.call("create", {"n_tx": nt, "n_rx": nr, "n_sc": L})
+    H_eng = np.transpose(hD, (2, 1, 0))[None]                                              # [1, Nr, Nt, L]
+    for ns, nrf in ((1, 1), (2, 3)):
+        Fbb, Frf, idx = mex.call("omphyb", hD, float(ns), float(nrf), AtExp, nlhs=3)
+        # MATLAB drops trailing singleton dimensions ([L x 1 x 1] is [L x 1]): compare the element counts, then view
+        assert Fbb.size == L * ns * nrf and Frf.size == L * nrf * nt and idx.size == L * nrf
+        assert Fbb.shape[0] == L and Frf.shape[0] == L and idx.shape[0] == L
+        Fbb, Frf, idx = Fbb.reshape(L, ns, nrf), Frf.reshape(L, nrf, nt), idx.reshape(L, nrf)
+        r_idx, r_fbb, _, _ = oomp.omp_precoder(H_eng, At, ns, nrf)
+        assert np.array_equal(idx.T.astype(np.int64) - 1, r_idx[0])                        # 1-based columns
+        for k in range(L):
+            assert np.array_equal(Frf[k], At[:, r_idx[0, :, k]].T)                         # Frf_out = Frf.' (:197)
+            M = Frf[k].T @ Fbb[k].T                                                        # Frf*Fbb in the reference's convention
+            Mr = At[:, r_idx[0, :, k]] @ r_fbb[0, :, :, k].T
+            assert np.max(np.abs(M @ M.conj().T - Mr @ Mr.conj().T)) <= 1e-9
+            assert abs(np.linalg.norm(M) - np.sqrt(ns)) <= 1e-10                           # :179
+        Fbb2, Frf2 = mex.call("omphyb", hD, float(ns), float(nrf), At, nlhs=2)             # 2-D dictionary form
+        assert np.array_equal(Fbb, Fbb2.reshape(Fbb.shape)) and np.array_equal(Frf, Frf2.reshape(Frf.shape))
+    for bad, ident in (((hD[:, :, :1], 1.0, 1.0, At), "mamimo:size"), ((hD, 3.0, 3.0, At), "mamimo:size"),
+                       ((hD, 1.0, 1.0, At[:5]), "mamimo:size"), ((hD.real, 1.0, 1.0, At), "mamimo:type")):
+        with pytest.raises(MexError) as ei:
+            mex.call("omphyb", *bad, nlhs=2)
+        assert ei.value.identifier == ident
+    mex.call("destroy")
