@@ -136,3 +136,31 @@ def test_errors():
             eng.omp(F, 1, 11)                                      # more RF chains than dictionary columns / > 8
         with pytest.raises(ValueError):
             eng.omp(F, 3, 1)                                       # ns > rows of F
+
+
+def test_full_size_properties_and_sampled_oracle():
+    """BASELINE configs[1] shape with the reference's dictionary size (32x4x1024, 500 rays, Ns = 1, NtRF = 4 to exercise
+    the rounds): size-independent properties on every tone -- columns never repeat (the residual is orthogonal to the
+    chosen ones), the residual norm never grows, ||Frf*Fbb||_F = sqrt(Ns) -- and the oracle on a sample of tones."""
+    import torch
+    nt, nr, nsc, npkt, ns, nrf, nrays = 32, 4, 1024, 24, 1, 4, 500
+    rng = np.random.default_rng(2024)
+    _, H = mm.synth.make_packets(75, npkt, nt, nr, nsc, snr_db=10.0, dtype=np.complex128)
+    At = np.exp(2j * np.pi * rng.random((nt, nrays)))
+    with mm.Engine(nt, nr, nsc, mlp=False, max_pkts=npkt) as eng:
+        eng.set_steering_dictionary(At)
+        Hd = torch.from_numpy(H).cuda()
+        _, V = eng.svd(Hd)
+        idx, err, Fbb = (t.cpu().numpy() for t in eng.omp(V, ns, nrf))
+        V = V.cpu().numpy()
+    assert idx.min() >= 0 and idx.max() < nrays
+    srt = np.sort(idx, axis=1)
+    assert np.all(np.diff(srt, axis=1) > 0)                                  # four distinct columns per tone
+    assert np.all(np.diff(err, axis=1) <= 1e-6)
+    A = At[:, idx]                                                           # [nt, npkt, nrf, nsc]
+    M = np.einsum("tpjk,psjk->ptsk", A, Fbb)                                 # Frf*Fbb per tone: [npkt, nt, ns, nsc]
+    assert np.max(np.abs(np.sqrt(np.sum(np.abs(M) ** 2, axis=(1, 2))) - np.sqrt(ns))) <= 1e-10
+    for p, k in zip(rng.integers(0, npkt, 48), rng.integers(0, nsc, 48)):
+        fb, _, ix, e = oomp.precoder_for_subcarrier(V[p, :ns, :, k].T, At, nrf)
+        assert np.array_equal(idx[p, :, k], ix) and abs(err[p, -1, k] - e) <= 1e-6
+        assert np.max(np.abs(Fbb[p, :, :, k] - fb)) <= 1e-11
