@@ -2215,8 +2215,10 @@ mamimo_status mamimo_omp(mamimo_engine* e, const void* F, mamimo_ctype f_type, i
   const int pf = (nt * kOmpTile + kOmpThreads - 1) / kOmpThreads;          // = ceil(n_tx / 4)
   auto corr = pf <= 8 ? omp_corr_kernel<8> : (pf <= 16 ? omp_corr_kernel<16> : omp_corr_kernel<25>);
   CK(e, cudaFuncSetAttribute(corr, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(corr_smem)));
-  CK(e, cudaFuncSetAttribute(omp_corr1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(omp_corr1_smem(nt))));
   e->omp_generic = getenv("MAMIMO_OMP_GENERIC") != nullptr;     // diagnostics: the 4x4 kernel for Ns = 1 too
+  const bool tall = ns == 1 && !e->omp_generic && omp_corr1_smem(nt) <= kOmpSmemBudget;
+  if (tall)
+    CK(e, cudaFuncSetAttribute(omp_corr1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(omp_corr1_smem(nt))));
   auto stage = [&](int64_t n, const void* in0, const void*, void* fbb, float* ix, float* er, cudaStream_t st) {
     OmpArgs a;
     memset(&a, 0, sizeof(a));
@@ -2233,7 +2235,7 @@ mamimo_status mamimo_omp(mamimo_engine* e, const void* F, mamimo_ctype f_type, i
       a.round = r;
       {
         ProfScope ps(e, st, kClsStage);
-        if (ns == 1 && !e->omp_generic) omp_corr1_kernel<<<grid_c, kOmp1Threads, omp_corr1_smem(nt), st>>>(a);
+        if (tall) omp_corr1_kernel<<<grid_c, kOmp1Threads, omp_corr1_smem(nt), st>>>(a);
         else corr<<<grid_c, kOmpThreads, corr_smem, st>>>(a, w_res);
       }
       {

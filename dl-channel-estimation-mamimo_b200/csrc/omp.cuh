@@ -63,6 +63,15 @@ __device__ __forceinline__ double2 cmulc(const double2 a, const double2 b) {    
 constexpr size_t kOmpSmemBudget = 200 * 1024;
 inline size_t omp_tile_bytes(int n_tx) { return static_cast<size_t>(n_tx) * kOmpTile * sizeof(double2); }
 inline bool omp_w_resident(int n_tx, int ns) { return (2 + static_cast<size_t>(ns)) * omp_tile_bytes(n_tx) <= kOmpSmemBudget; }
+// 16-byte asynchronous copy global -> shared (LDGSTS; no register staging), committed / awaited per thread
+__device__ __forceinline__ void omp_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void omp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void omp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 inline size_t omp_corr_smem(int n_tx, int ns) { return (2 + (omp_w_resident(n_tx, ns) ? ns : 1)) * omp_tile_bytes(n_tx); }
 constexpr int kOmpMaxTx = 100;        // 3 tiles of n_tx x 64 complex doubles within the budget
 
@@ -188,17 +197,17 @@ __global__ void __launch_bounds__(kOmpThreads) omp_corr_kernel(const OmpArgs a, 
 // Ns = 1 (the reference's own use: numSTS = 1, pg/generate_maMIMO_LTF.m:23) -- no energy sum over columns, so the
 // registers it would take go into a taller block: 8 rays x 4 tones per thread (12 shared-memory loads per 32 complex
 // FMAs instead of 8 per 16: a 128-bit shared load costs 4 wavefronts per warp whatever it fetches, and at 4x4 the
-// load pipe is as busy as the FP64 pipe).  128 threads, one conj(At) buffer, two CTAs per SM: one loads while the other
-// contracts.
+// load pipe is as busy as the FP64 pipe).  128 threads, two CTAs per SM; the next conj(At) chunk arrives by cp.async
+// (LDGSTS) in a second buffer while the current one is contracted.
 constexpr int kOmp1Threads = 128;
-inline size_t omp_corr1_smem(int n_tx) { return 2 * omp_tile_bytes(n_tx); }
+inline size_t omp_corr1_smem(int n_tx) { return 3 * omp_tile_bytes(n_tx); }
 
 __global__ void __launch_bounds__(kOmp1Threads, 2) omp_corr1_kernel(const OmpArgs a) {
   extern __shared__ __align__(16) unsigned char omp_smem[];
   const int nt = a.n_tx;
   const int tile = nt * kOmpTile;
-  double2* As = reinterpret_cast<double2*>(omp_smem);                 // [n_tx][64] conj(At) chunk
-  double2* Ws = As + static_cast<size_t>(tile);                       // [n_tx][64] residual of 64 tones
+  double2* As = reinterpret_cast<double2*>(omp_smem);                 // [2][n_tx][64] conj(At) chunks
+  double2* Ws = As + 2 * static_cast<size_t>(tile);                   // [n_tx][64] residual of 64 tones
   __shared__ double red_e[8][kOmpTile];
   __shared__ int red_r[8][kOmpTile];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;          // ty 0..7: rays ty + 8 i
@@ -208,6 +217,12 @@ __global__ void __launch_bounds__(kOmp1Threads, 2) omp_corr1_kernel(const OmpArg
   const size_t src_rows = first ? a.f_rows : 1;
   const void* src = first ? a.F : a.Wres;
   const int src_double = first ? a.f_double : 1;
+  auto fetch = [&](int c0, double2* dst) {
+    for (int i = tid; i < tile; i += kOmp1Threads)
+      omp_cp_async16(dst + i, a.AtcT + static_cast<size_t>(i / kOmpTile) * a.n_rays_pad + c0 + i % kOmpTile);
+    omp_cp_async_commit();
+  };
+  fetch(0, As);
   for (int i = tid; i < tile; i += kOmp1Threads) {
     const int t = i / kOmpTile, k = k0 + i % kOmpTile;
     Ws[i] = k < a.n_sc ? omp_ld(src, (pkt * src_rows * nt + t) * static_cast<size_t>(a.n_sc) + k, src_double)
@@ -217,20 +232,22 @@ __global__ void __launch_bounds__(kOmp1Threads, 2) omp_corr1_kernel(const OmpArg
   int best_r[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) { best_e[j] = -1.0; best_r[j] = 0; }
-  for (int c0 = 0; c0 < a.n_rays_pad; c0 += kOmpTile) {
-    __syncthreads();
-    for (int i = tid; i < tile; i += kOmp1Threads)
-      As[i] = __ldg(a.AtcT + static_cast<size_t>(i / kOmpTile) * a.n_rays_pad + c0 + i % kOmpTile);
-    __syncthreads();
+  int buf = 0;
+  for (int c0 = 0; c0 < a.n_rays_pad; c0 += kOmpTile, buf ^= 1) {
+    omp_cp_async_wait_all();
+    __syncthreads();                    // chunk c0 has landed for everyone; nobody still reads the other buffer
+    if (c0 + kOmpTile < a.n_rays_pad) fetch(c0 + kOmpTile, As + static_cast<size_t>(buf ^ 1) * tile);
+    const double2* Ac = As + static_cast<size_t>(buf) * tile;
     double2 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0.0, 0.0);
+#pragma unroll 2
     for (int t = 0; t < nt; ++t) {
       double2 av[8], wv[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) av[i] = As[t * kOmpTile + ty + 8 * i];
+      for (int i = 0; i < 8; ++i) av[i] = Ac[t * kOmpTile + ty + 8 * i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) wv[j] = Ws[t * kOmpTile + tx + 16 * j];
 #pragma unroll
