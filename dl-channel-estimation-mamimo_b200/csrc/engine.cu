@@ -77,6 +77,7 @@ struct mamimo_engine {
   int host_chunk = 0;           // units per chunk of the host-buffer pipeline
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
+  bool fc_small = true;         // few-row calls: 128 x 128 tiles on single CTAs instead (MAMIMO_FC_SMALL=0 disables)
   bool ofdm_tma = true;         // persistent bulk-copy-fed OFDM kernel (MAMIMO_OFDM_TMA=0: plain three-pass kernel)
   bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
   int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
@@ -272,6 +273,7 @@ mamimo_status make_map(mamimo_engine* e, CUtensorMap* map, const Operand& op, in
 }
 
 constexpr int kTcBN = 256;
+constexpr int kTcSmallBN = 128;   // few-row calls (a handful of packets): 128 x 128 tiles on single CTAs
 constexpr int kDynSlots = kDynSlotsMax;
 static_assert(kMaxLevels >= MAMIMO_MAX_HIDDEN + 1, "DynState levels");
 
@@ -314,6 +316,9 @@ mamimo_status set_tc_attr(mamimo_engine* e) {
   using Cfg = FcTcCfg<S, kTcBN>;
   const int smem = Cfg::kStages * Cfg::kStageBytes + Cfg::kAuxBytes + 1024;
   CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  using CfgS = FcTcCfg<S, kTcSmallBN>;
+  CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcSmallBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             CfgS::kStages * CfgS::kStageBytes + CfgS::kAuxBytes + 1024));
   using Cfg2 = FcTc2Cfg<S>;
   const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
   CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -468,6 +473,19 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
     const int grid = ((a.M + 127) / 128) * ((a.N + 127) / 128);
     fc_simt_kernel<S><<<grid, 256, 0, st>>>(a);
   } else {
+    // Latency regime: a call of a few packets gives the CTA-pair kernel only ceil(N/256) tiles per layer (one packet:
+    // 4 pairs, half of each pair on rows that do not exist) and every tile walks the whole K serially.  128 x 128
+    // tiles on single CTAs double the number of SMs at work and halve the MMA time per tile; the accumulation order per
+    // output element is the same, so the results are bit-identical to the pair kernel's.
+    const int small_tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcSmallBN - 1) / kTcSmallBN);
+    if (e->fc_pair && e->fc_small && !gm && a.row_off == 0 && small_tiles * 2 <= e->fc_sms) {
+      using CfgS = FcTcCfg<S, kTcSmallBN>;
+      const int smem = CfgS::kStages * CfgS::kStageBytes + CfgS::kAuxBytes + 1024;
+      fc_tc_kernel<S, kTcSmallBN><<<small_tiles, kFcThreads, smem, st>>>(d.tmap_a, d.tmap_b_half, a);
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches++;
+      return MAMIMO_OK;
+    }
     if (e->fc_pair) {
       using Cfg2 = FcTc2Cfg<S>;
       const int pair_tiles = ((a.M + 2 * kFcBlockM - 1) / (2 * kFcBlockM)) * ((a.N + kTcBN - 1) / kTcBN);
@@ -1071,6 +1089,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   if (const char* env = getenv("MAMIMO_KB_PER_CHUNK")) { if (atoi(env) > 0) e->kb_per_chunk = atoi(env); }
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_FC_SMALL")) e->fc_small = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
