@@ -961,3 +961,24 @@ def test_device_path_replays_as_one_cuda_graph():
         eng.estimate_raw(Yd.data_ptr(), 0, npkt, 0, Hr.data_ptr(), Hi.data_ptr(), 1, st.cuda_stream)
         st.synchronize()
         assert torch.equal(Hr, Hr0)
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3"])
+@pytest.mark.parametrize("nt,nr,nsc,hidden,npkt", [(32, 4, 1024, (1024, 1024), 1), (32, 4, 1024, (1024, 1024), 3),
+                                                  (8, 2, 234, (96, 160), 5)])
+def test_few_row_tiles_bitwise_equal_pair_kernel(nt, nr, nsc, hidden, npkt, precision, monkeypatch):
+    """Few-row calls run 128 x 128 tiles on single CTAs instead of 256 x 256 CTA-pair tiles (latency): the accumulation
+    order per output element is the same, so both must return the same bits -- and the oracle's values."""
+    x = mm.synth.make_pilots(nsc)
+    nets = mm.synth.make_nets(nsc, hidden, nsc)
+    Y, _ = mm.synth.make_packets(33, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
+    outs = []
+    for small in ("1", "0"):
+        monkeypatch.setenv("MAMIMO_FC_SMALL", small)
+        with mm.Engine(nt, nr, nsc, hidden=hidden, precision=precision) as eng:
+            eng.set_pilots(x, None)
+            eng.load_weights(nets)
+            outs.append(eng.estimate(Y))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    _, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
+    assert rel_l2(ref_r + 1j * ref_i, outs[0][0].astype(np.float64) + 1j * outs[0][1]) <= TOL_DNN
