@@ -914,6 +914,33 @@ mamimo_status run_chunked(mamimo_engine* e, int64_t n_units, int64_t units_per_c
   mamimo_status s = ensure_staging(e, cu * in0_unit_bytes, in1 ? cu * in1_unit_bytes : 0, hr ? cu * h_unit_bytes : 0,
                                    hls ? cu * hls_unit_bytes : 0);
   if (s != MAMIMO_OK) return s;
+  if (n_units <= units_per_chunk) {
+    // one chunk (latency regime): nothing to overlap, so copy in, compute and copy out on ONE stream -- no event
+    // hand-offs between streams
+    cudaStream_t st = e->s_comp;
+    CK(e, cudaMemcpyAsync(e->st_in[0], in0, n_units * in0_unit_bytes, cudaMemcpyHostToDevice, st));
+    e->stats.h2d_bytes += n_units * in0_unit_bytes;
+    if (in1) {
+      CK(e, cudaMemcpyAsync(e->st_in2[0], in1, n_units * in1_unit_bytes, cudaMemcpyHostToDevice, st));
+      e->stats.h2d_bytes += n_units * in1_unit_bytes;
+    }
+    s = stage(n_units, e->st_in[0], in1 ? e->st_in2[0] : nullptr, hls ? e->st_hls[0] : nullptr, hr ? e->st_hr[0] : nullptr,
+              hi ? e->st_hi[0] : nullptr, st);
+    if (s != MAMIMO_OK) return s;
+    if (hls) {
+      CK(e, cudaMemcpyAsync(hls, e->st_hls[0], n_units * hls_unit_bytes, cudaMemcpyDeviceToHost, st));
+      e->stats.d2h_bytes += n_units * hls_unit_bytes;
+    }
+    if (hr) {
+      CK(e, cudaMemcpyAsync(hr, e->st_hr[0], n_units * h_unit_bytes, cudaMemcpyDeviceToHost, st));
+      e->stats.d2h_bytes += n_units * h_unit_bytes;
+      if (hi) {
+        CK(e, cudaMemcpyAsync(hi, e->st_hi[0], n_units * h_unit_bytes, cudaMemcpyDeviceToHost, st));
+        e->stats.d2h_bytes += n_units * h_unit_bytes;
+      }
+    }
+    return check_flags(e, st);          // copies the flag word behind the outputs and synchronises the stream
+  }
   int64_t c = 0;
   for (int64_t u0 = 0; u0 < n_units; u0 += units_per_chunk, ++c) {
     const int b = static_cast<int>(c & 1);
