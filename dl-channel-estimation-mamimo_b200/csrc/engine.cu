@@ -40,6 +40,7 @@ struct DevLayer {
   float rowsum = 0.f, bmax = 0.f;   // max_n sum_k |W[k][n]| and max_n |b[n]| of the folded layer (FP16X3 range bounds)
   CUtensorMap tmap_b;       // box of 256 weight rows (1-CTA kernel)
   CUtensorMap tmap_b_half;  // box of 128 weight rows (CTA-pair kernel: each CTA stages half the tile)
+  CUtensorMap tmap_b_q;     // box of 64 weight rows (few-row calls: 128 x 64 tiles)
   CUtensorMap tmap_a;      // A operand of this layer (net-specific buffer for layer 0)
 };
 
@@ -78,6 +79,7 @@ struct mamimo_engine {
   int kb_per_chunk = 4;
   bool fc_pair = true;          // CTA-pair (cta_group::2) FC kernel
   bool fc_small = true;         // few-row calls: 128 x 128 tiles on single CTAs instead (MAMIMO_FC_SMALL=0 disables)
+  bool fc_tiny = true;          // and 128 x 64 tiles when even those leave most SMs idle (MAMIMO_FC_TINY=0 disables)
   bool ofdm_tma = true;         // persistent bulk-copy-fed OFDM kernel (MAMIMO_OFDM_TMA=0: plain three-pass kernel)
   bool ls_tma = true;           // TMA-fed persistent LS kernel (MAMIMO_LS_TMA=0: plain split kernel)
   int ls_tma_ctas = 4;          // resident CTAs per SM of that kernel (MAMIMO_LS_TMA_CTAS)
@@ -274,6 +276,7 @@ mamimo_status make_map(mamimo_engine* e, CUtensorMap* map, const Operand& op, in
 
 constexpr int kTcBN = 256;
 constexpr int kTcSmallBN = 128;   // few-row calls (a handful of packets): 128 x 128 tiles on single CTAs
+constexpr int kTcTinyBN = 64;     // one to four packets: 128 x 64 tiles
 constexpr int kDynSlots = kDynSlotsMax;
 static_assert(kMaxLevels >= MAMIMO_MAX_HIDDEN + 1, "DynState levels");
 
@@ -319,6 +322,9 @@ mamimo_status set_tc_attr(mamimo_engine* e) {
   using CfgS = FcTcCfg<S, kTcSmallBN>;
   CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcSmallBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              CfgS::kStages * CfgS::kStageBytes + CfgS::kAuxBytes + 1024));
+  using CfgT = FcTcCfg<S, kTcTinyBN>;
+  CK(e, cudaFuncSetAttribute(fc_tc_kernel<S, kTcTinyBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             CfgT::kStages * CfgT::kStageBytes + CfgT::kAuxBytes + 1024));
   using Cfg2 = FcTc2Cfg<S>;
   const int smem2 = Cfg2::kStages * Cfg2::kStageBytes + Cfg2::kAuxBytes + 1024;
   CK(e, cudaFuncSetAttribute(fc_tc2_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -478,6 +484,15 @@ mamimo_status launch_fc(mamimo_engine* e, const DevLayer& d, FcArgs a, cudaStrea
     // tiles on single CTAs double the number of SMs at work and halve the MMA time per tile; the accumulation order per
     // output element is the same, so the results are bit-identical to the pair kernel's.
     const int small_tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcSmallBN - 1) / kTcSmallBN);
+    const int tiny_tiles = ((a.M + kFcBlockM - 1) / kFcBlockM) * ((a.N + kTcTinyBN - 1) / kTcTinyBN);
+    if (e->fc_pair && e->fc_small && e->fc_tiny && !gm && a.row_off == 0 && tiny_tiles * 2 <= e->fc_sms) {
+      using CfgT = FcTcCfg<S, kTcTinyBN>;       // one to four packets: 128 x 64 tiles, twice the SMs again
+      const int smem = CfgT::kStages * CfgT::kStageBytes + CfgT::kAuxBytes + 1024;
+      fc_tc_kernel<S, kTcTinyBN><<<tiny_tiles, kFcThreads, smem, st>>>(d.tmap_a, d.tmap_b_q, a);
+      CK(e, cudaGetLastError());
+      e->stats.kernel_launches++;
+      return MAMIMO_OK;
+    }
     if (e->fc_pair && e->fc_small && !gm && a.row_off == 0 && small_tiles * 2 <= e->fc_sms) {
       using CfgS = FcTcCfg<S, kTcSmallBN>;
       const int smem = CfgS::kStages * CfgS::kStageBytes + CfgS::kAuxBytes + 1024;
@@ -1117,6 +1132,7 @@ mamimo_status mamimo_create(const mamimo_config* cfg, mamimo_engine** out) {
   e->fc_pair = cfg->fc_single_cta == 0;
   if (const char* env = getenv("MAMIMO_FC_PAIR")) e->fc_pair = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_FC_SMALL")) e->fc_small = atoi(env) != 0;
+  if (const char* env = getenv("MAMIMO_FC_TINY")) e->fc_tiny = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_L2_PREFETCH")) e->l2_prefetch = atoi(env);
   if (const char* env = getenv("MAMIMO_LS_SPLIT")) e->ls_split = atoi(env) != 0;
   if (const char* env = getenv("MAMIMO_GRAPH")) e->use_graphs = atoi(env) != 0;
@@ -1383,6 +1399,8 @@ mamimo_status mamimo_finalize_weights(mamimo_engine* e) {
         s = make_map(e, &d.tmap_b, d.w, d.w.kpad, kTcBN);
         if (s != MAMIMO_OK) return s;
         s = make_map(e, &d.tmap_b_half, d.w, d.w.kpad, kTcBN / 2);
+        if (s != MAMIMO_OK) return s;
+        s = make_map(e, &d.tmap_b_q, d.w, d.w.kpad, kTcTinyBN);
         if (s != MAMIMO_OK) return s;
         const Operand& A = (l == 0) ? e->act_in[net] : e->act_h[net][(l - 1) & 1];
         s = make_map(e, &d.tmap_a, A, d.K, kFcBlockM);

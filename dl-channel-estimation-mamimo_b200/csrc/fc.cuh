@@ -118,7 +118,7 @@ struct FcTcCfg {
   static constexpr int kColsPerThread = BN / 2;              // each epilogue thread: one row, half the columns
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
   static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "power-of-two TMEM allocation");
-  static_assert(kColsPerThread % 64 == 0, "drain granularity is 64 columns");
+  static_assert(kColsPerThread == 32 || kColsPerThread % 64 == 0, "drain granularity is 64 columns (32 for BN = 64)");
 };
 
 // One 32-column group of one row: bias, activation, then either split planes or float32.
@@ -342,17 +342,30 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (!mbar_wait(tfull_bar + acc, acc_phase, cta_abort, a.flags)) { ok = false; break; }
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * Cfg::kColsPerThread;
-#pragma unroll
-        for (int g = 0; g < kGroups; g += 2) {      // 64 columns per TMEM load
-          uint32_t r[64];
-          tmem_ld64(taddr + g * 32, r);
+        if constexpr (kGroups == 1) {               // 64-column tiles (few-row calls): one 32-column drain per thread
+          uint32_t r[32];
+          tmem_ld32(taddr, r);
           tmem_ld_wait();
           if (c == 0) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[0][j] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] += __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sum[0][j] += __uint_as_float(r[j]);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < kGroups; g += 2) {      // 64 columns per TMEM load
+            uint32_t r[64];
+            tmem_ld64(taddr + g * 32, r);
+            tmem_ld_wait();
+            if (c == 0) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) sum[g + (j >> 5)][j & 31] += __uint_as_float(r[j]);
+            }
           }
         }
         tc_fence_before_sync();

@@ -973,12 +973,14 @@ def test_few_row_tiles_bitwise_equal_pair_kernel(nt, nr, nsc, hidden, npkt, prec
     nets = mm.synth.make_nets(nsc, hidden, nsc)
     Y, _ = mm.synth.make_packets(33, npkt, nt, nr, nsc, snr_db=10.0, x_tones=x)
     outs = []
-    for small in ("1", "0"):
+    for small, tiny in (("1", "1"), ("1", "0"), ("0", "0")):       # 128 x 64 tiles, 128 x 128 tiles, CTA-pair 256 x 256
         monkeypatch.setenv("MAMIMO_FC_SMALL", small)
+        monkeypatch.setenv("MAMIMO_FC_TINY", tiny)
         with mm.Engine(nt, nr, nsc, hidden=hidden, precision=precision) as eng:
             eng.set_pilots(x, None)
             eng.load_weights(nets)
             outs.append(eng.estimate(Y))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
     _, ref_r, ref_i = oracle_full(Y, tables.sylvester_hadamard(nt), x, 1, nets)
     assert rel_l2(ref_r + 1j * ref_i, outs[0][0].astype(np.float64) + 1j * outs[0][1]) <= TOL_DNN
