@@ -2195,10 +2195,10 @@ mamimo_status mamimo_svd(mamimo_engine* e, const void* H, mamimo_ctype h_type, i
   CK(e, cudaFuncSetAttribute(svd_gram_smem_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, svd_smem_bytes<NR>())); \
   svd_gram_smem_kernel<NR><<<grid_s, kSvdSmemThreads, svd_smem_bytes<NR>(), st>>>(a);
     switch (nr) {
-      case 1: svd_gram_kernel<1><<<grid, 128, 0, st>>>(a); break;
-      case 2: svd_gram_kernel<2><<<grid, 128, 0, st>>>(a); break;
-      case 3: svd_gram_kernel<3><<<grid, 128, 0, st>>>(a); break;
-      case 4: svd_gram_kernel<4><<<grid, 128, 0, st>>>(a); break;
+      case 1: if (a.h_double) svd_gram_kernel<1, true><<<grid, 128, 0, st>>>(a); else svd_gram_kernel<1, false><<<grid, 128, 0, st>>>(a); break;
+      case 2: if (a.h_double) svd_gram_kernel<2, true><<<grid, 128, 0, st>>>(a); else svd_gram_kernel<2, false><<<grid, 128, 0, st>>>(a); break;
+      case 3: if (a.h_double) svd_gram_kernel<3, true><<<grid, 128, 0, st>>>(a); else svd_gram_kernel<3, false><<<grid, 128, 0, st>>>(a); break;
+      case 4: if (a.h_double) svd_gram_kernel<4, true><<<grid, 128, 0, st>>>(a); else svd_gram_kernel<4, false><<<grid, 128, 0, st>>>(a); break;
       case 5: { SVD_SMEM_CASE(5) } break;
       case 6: { SVD_SMEM_CASE(6) } break;
       case 7: { SVD_SMEM_CASE(7) } break;

@@ -37,7 +37,8 @@ __device__ __forceinline__ double2 svd_ld(const void* H, size_t idx, int is_doub
   return make_double2(v.x, v.y);
 }
 
-template <int NR>
+// HD: H is complex128 (compile-time, so the column loads are straight-line code the compiler can batch)
+template <int NR, bool HD>
 __global__ void __launch_bounds__(128) svd_gram_kernel(const SvdArgs a) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n_sc) return;
@@ -51,10 +52,13 @@ __global__ void __launch_bounds__(128) svd_gram_kernel(const SvdArgs a) {
   for (int i = 0; i < NR; ++i)
 #pragma unroll
     for (int j = 0; j < NR; ++j) G[i][j] = make_double2(0.0, 0.0);
+  // the loads of several columns in flight per thread: at 2 CTAs of 128 threads per SM the kernel is bound by memory
+  // latency, not by bandwidth or FP64 rate
+#pragma unroll 4
   for (int t = 0; t < a.n_tx; ++t) {
     double2 h[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) h[i] = svd_ld(a.H, base + i * rx_stride + static_cast<size_t>(t) * a.n_sc, a.h_double);
+    for (int i = 0; i < NR; ++i) h[i] = svd_ld(a.H, base + i * rx_stride + static_cast<size_t>(t) * a.n_sc, HD ? 1 : 0);
 #pragma unroll
     for (int i = 0; i < NR; ++i)
 #pragma unroll
@@ -95,23 +99,28 @@ __global__ void __launch_bounds__(128) svd_gram_kernel(const SvdArgs a) {
         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
         const double c = rsqrt(1.0 + t * t), s = t * c;
         const double sr = s * phr, si = s * phi;                           // s e^{i phi}
+        // G <- J^H G J touches rows / columns p and q only, and G stays Hermitian: update column entries (m, p), (m, q)
+        // for m outside {p, q}, mirror them into rows p and q, and set the 2 x 2 block in closed form
+        // (G_pq' = 0, G_pp' = G_pp - t b, G_qq' = G_qq + t b) -- half the multiplies of the two-sided product.
 #pragma unroll
-        for (int m = 0; m < NR; ++m) {                                     // columns p, q of G and U
-          const double2 gp = G[m][p], gq = G[m][q];
-          // col p' = c gp - conj(se) gq ; col q' = se gp + c gq
-          G[m][p] = make_double2(c * gp.x - (sr * gq.x + si * gq.y), c * gp.y - (sr * gq.y - si * gq.x));
-          G[m][q] = make_double2(sr * gp.x - si * gp.y + c * gq.x, sr * gp.y + si * gp.x + c * gq.y);
+        for (int m = 0; m < NR; ++m) {
+          if (m != p && m != q) {
+            const double2 gp = G[m][p], gq = G[m][q];
+            // col p' = c gp - conj(se) gq ; col q' = se gp + c gq
+            const double2 np_ = make_double2(c * gp.x - (sr * gq.x + si * gq.y), c * gp.y - (sr * gq.y - si * gq.x));
+            const double2 nq = make_double2(sr * gp.x - si * gp.y + c * gq.x, sr * gp.y + si * gp.x + c * gq.y);
+            G[m][p] = np_; G[m][q] = nq;
+            G[p][m] = make_double2(np_.x, -np_.y);
+            G[q][m] = make_double2(nq.x, -nq.y);
+          }
           const double2 up = U[m][p], uq = U[m][q];
           U[m][p] = make_double2(c * up.x - (sr * uq.x + si * uq.y), c * up.y - (sr * uq.y - si * uq.x));
           U[m][q] = make_double2(sr * up.x - si * up.y + c * uq.x, sr * up.y + si * up.x + c * uq.y);
         }
-#pragma unroll
-        for (int m = 0; m < NR; ++m) {                                     // rows p, q of G
-          const double2 gp = G[p][m], gq = G[q][m];
-          // row p' = c gp - se gq ; row q' = conj(se) gp + c gq
-          G[p][m] = make_double2(c * gp.x - (sr * gq.x - si * gq.y), c * gp.y - (sr * gq.y + si * gq.x));
-          G[q][m] = make_double2(sr * gp.x + si * gp.y + c * gq.x, sr * gp.y - si * gp.x + c * gq.y);
-        }
+        G[p][p].x -= t * b; G[q][q].x += t * b;
+        G[p][p].y = 0.0; G[q][q].y = 0.0;
+        G[p][q] = make_double2(0.0, 0.0);
+        G[q][p] = make_double2(0.0, 0.0);
       }
   }
 
@@ -137,10 +146,13 @@ __global__ void __launch_bounds__(128) svd_gram_kernel(const SvdArgs a) {
   if (!a.V1) return;
 
   // ---- pass 2: V1[t][r] = sum_i conj(H[i][t]) U[i][ord r] / sigma_r
+  // the loads of several columns in flight per thread: at 2 CTAs of 128 threads per SM the kernel is bound by memory
+  // latency, not by bandwidth or FP64 rate
+#pragma unroll 4
   for (int t = 0; t < a.n_tx; ++t) {
     double2 h[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) h[i] = svd_ld(a.H, base + i * rx_stride + static_cast<size_t>(t) * a.n_sc, a.h_double);
+    for (int i = 0; i < NR; ++i) h[i] = svd_ld(a.H, base + i * rx_stride + static_cast<size_t>(t) * a.n_sc, HD ? 1 : 0);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       double vx = 0.0, vy = 0.0;

@@ -79,7 +79,9 @@ def test_svd_reference_lines_golden_on_gpu(golden_dir):
         for k in range(n):
             H = Hin[k].T
             s_ref = np.array([np.linalg.norm(H @ Fopt[k][:, r]) for r in range(nr)])
-            assert np.allclose(sigma[0, :, k], s_ref, rtol=1e-9, atol=1e-9 * s_ref[0]), (tag, k)
+            # absolute floor: the Gram route resolves sigma_r only down to ~sqrt(eps) * sigma_1 (svd.cuh header); the
+            # rank-deficient golden matrix has sigma_4 = 1e-15 and comes back as rounding noise of that size
+            assert np.allclose(sigma[0, :, k], s_ref, rtol=1e-9, atol=1e-7 * s_ref[0]), (tag, k)
             rank = int(np.sum(s_ref > 1e-6 * s_ref[0]))
             Pk = osvd.projector(V1[:, :rank])[0][k]
             assert np.linalg.norm(Pk - osvd.projector_from_fopt(Fopt[k], rank)) <= 1e-7 * np.sqrt(rank), (tag, k)
