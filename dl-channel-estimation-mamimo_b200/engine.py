@@ -381,11 +381,13 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ per-subcarrier SVD
-    def svd(self, H, want_vectors=True, check_flags=True):
+    def svd(self, H, want_vectors=True, check_flags=True, out_double=None):
         """Singular values and dominant right singular vectors of every per-tone [n_rx x n_tx] channel matrix
         (pg/omphybweights.m:174-176: H = Hin.'; [~,~,v] = svd(H)).  H [n_pkt, n_rx, n_tx, n_sc] complex64/128 (numpy =
         host, torch CUDA = device) -> sigma [n_pkt, n_rx, n_sc] (descending along axis 1) and V1 [n_pkt, n_rx, n_tx, n_sc]
-        with V1[p, r, :, k] = v_r of tone k (unique up to a phase; V1 V1^H is the projector onto the row space)."""
+        with V1[p, r, :, k] = v_r of tone k (unique up to a phase; V1 V1^H is the projector onto the row space).
+        out_double: precision of sigma / V1 (None = that of H; True = float64 / complex128 whatever H is -- the
+        arithmetic is FP64 either way)."""
         c = self.cfg
         if tuple(H.shape[1:]) != (c.n_rx, c.n_tx, c.n_sc):
             raise ValueError("H must be [n_pkt, n_rx=%d, n_tx=%d, n_sc=%d]" % (c.n_rx, c.n_tx, c.n_sc))
@@ -396,12 +398,14 @@ class Engine:
                 raise TypeError("H must be complex64 or complex128")
             H = H.contiguous()
             dbl = H.dtype == torch.complex128
-            sig = torch.empty((n_pkt, c.n_rx, c.n_sc), dtype=torch.float64 if dbl else torch.float32, device=H.device)
-            V = torch.empty_like(H) if want_vectors else None
+            odbl = dbl if out_double is None else bool(out_double)
+            sig = torch.empty((n_pkt, c.n_rx, c.n_sc), dtype=torch.float64 if odbl else torch.float32, device=H.device)
+            V = torch.empty(H.shape, dtype=torch.complex128 if odbl else torch.complex64, device=H.device) if want_vectors else None
             t = _capi.C128 if dbl else _capi.C64
+            to = _capi.C128 if odbl else _capi.C64
             st = torch.cuda.current_stream(H.device).cuda_stream
             check(lib.mamimo_svd(self._h, C.c_void_p(H.data_ptr()), t, n_pkt, C.c_void_p(sig.data_ptr()),
-                                 C.c_void_p(V.data_ptr()) if want_vectors else None, t, _capi.MEM_DEVICE, C.c_void_p(st)), self._h)
+                                 C.c_void_p(V.data_ptr()) if want_vectors else None, to, _capi.MEM_DEVICE, C.c_void_p(st)), self._h)
             if check_flags:
                 self.poll_flags(st)
             return (sig, V) if want_vectors else sig
@@ -409,10 +413,12 @@ class Engine:
         if H.dtype not in (np.complex64, np.complex128):
             raise TypeError("H must be complex64 or complex128")
         dbl = H.dtype == np.complex128
+        odbl = dbl if out_double is None else bool(out_double)
         t = _capi.C128 if dbl else _capi.C64
-        sig = np.empty((n_pkt, c.n_rx, c.n_sc), dtype=np.float64 if dbl else np.float32)
-        V = np.empty_like(H) if want_vectors else None
-        check(lib.mamimo_svd(self._h, _np_ptr(H), t, n_pkt, _np_ptr(sig), _np_ptr(V) if want_vectors else None, t,
+        to = _capi.C128 if odbl else _capi.C64
+        sig = np.empty((n_pkt, c.n_rx, c.n_sc), dtype=np.float64 if odbl else np.float32)
+        V = np.empty(H.shape, dtype=np.complex128 if odbl else np.complex64) if want_vectors else None
+        check(lib.mamimo_svd(self._h, _np_ptr(H), t, n_pkt, _np_ptr(sig), _np_ptr(V) if want_vectors else None, to,
                              _capi.MEM_HOST, None), self._h)
         return (sig, V) if want_vectors else sig
 
@@ -469,7 +475,7 @@ class Engine:
         """[Fbb, Frf] = omphybweights(hD, Ns, NtRF, AtExp) for a batch (pg/BER_test_maMIMO_LTF.m:372): svd() then omp().
         H [n_pkt, n_rx, n_tx, n_sc] -> (idx, err, Fbb) as omp(); the reference's Frf(k, j, :) is dictionary column
         idx[p, j, k]."""
-        _, V = self.svd(H)
+        _, V = self.svd(H, out_double=True)        # complex128 vectors: the column choice must not ride on FP32 rounding
         idx, err, Fbb = self.omp(V, ns, n_rf)
         return idx, err, Fbb
 
